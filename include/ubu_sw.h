@@ -1,0 +1,140 @@
+/* ubu_sw.h -- C ABI of the B200 Smith-Waterman realignment path (libubu_sw.so).
+ *
+ * Drop-in boundary for the reference's aligner facade. The reference side of this
+ * boundary is path-in/path-out and forks `bwa`:
+ *     new Aligner(String reference, int numThreads)   src/main/java/edu/unc/bioinf/ubu/assembly/Aligner.java:13-16
+ *     void align(String input, String outputSam)      Aligner.java:18-22   (bwa bwasw)
+ *     void shortAlign(String input, String outputSam) Aligner.java:46-56   (bwa aln + samse)
+ *     void index()                                    Aligner.java:62-69   (bwa index; no-op for window SW)
+ * called from ReAligner.alignAndCleanContigs (ReAligner.java:351-367) and
+ * ReAligner.alignToContigs (ReAligner.java:963-975). Nothing like a batch ABI exists in
+ * the reference, so the entry points below are BUILD-DEFINED; each
+ * comment names the reference interface it stands in for. INTEGRATION.md shows the JNI
+ * stub a maintainer would add under Aligner.
+ *
+ * Alignment semantics: SPEC.md (BUILD-DEFINED; reference parity UNPINNED).
+ * No torch / CUDA types cross this boundary: plain pointers and sizes only.
+ * Error convention: 0 on success, negative ubu_sw_status on failure, never throws or aborts
+ * (the reference throws RuntimeException on a non-zero bwa exit, Aligner.java:41-43; the JNI
+ * shim maps a non-zero status to the same exception).
+ * Threading: a handle is owned by one host thread at a time; distinct handles (one per GPU)
+ * are fully independent (the reference delegates parallelism with `-t numThreads`, Aligner.java:19,49).
+ */
+#ifndef UBU_SW_H
+#define UBU_SW_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBU_SW_VERSION 0x00010000u
+
+typedef enum {
+  UBU_SW_OK = 0,
+  UBU_SW_ERR_ARG = -1,          /* NULL pointer, bad parameter range, bad index          */
+  UBU_SW_ERR_CUDA = -2,         /* CUDA runtime failure; ubu_sw_last_error() has the text */
+  UBU_SW_ERR_CIGAR_POOL = -3,   /* cigar_pool_cap too small; *cigar_pool_used = required  */
+  UBU_SW_ERR_TOO_LONG = -4,     /* read longer than UBU_SW_MAX_READ                       */
+  UBU_SW_ERR_NO_DEVICE = -5,    /* no CUDA device / not an sm_100 device                  */
+  UBU_SW_ERR_BUSY = -6,         /* no free pipeline slot / ticket not pending             */
+  UBU_SW_ERR_NOMEM = -7
+} ubu_sw_status;
+
+#define UBU_SW_MAX_READ   256u      /* rows handled by the packed 16-bit kernel (all BASELINE configs: 50..250 bp) */
+#define UBU_SW_MAX_WINDOW 65535u
+
+/* SPEC.md section 1. Defaults +1 / -3 / 5 / 2. Stands in for bwa's (implicit, default) scoring flags. */
+typedef struct { int32_t match, mismatch, gap_open, gap_ext; } ubu_sw_params;
+
+/* SPEC.md section 6. Replaces the SAM fields the callers read back from bwa's output
+ * (POS, CIGAR, NM: ReAligner.java:1088-1143). 32 bytes. */
+typedef struct {
+  int32_t  score;
+  int32_t  ref_start, ref_end;     /* 1-based inclusive, within the window */
+  int32_t  q_start, q_end;         /* 1-based inclusive, within the read   */
+  int32_t  edit_distance;          /* = NM (ReAligner.java:282-285)        */
+  uint32_t cigar_off;              /* first op in the CIGAR pool           */
+  uint16_t cigar_n;                /* number of ops                        */
+  uint16_t flags;                  /* UBU_SW_FLAG_*                        */
+} ubu_sw_result;
+
+#define UBU_SW_FLAG_UNALIGNED 1u
+#define UBU_SW_CIGAR_M 0u
+#define UBU_SW_CIGAR_I 1u
+#define UBU_SW_CIGAR_D 2u
+#define UBU_SW_CIGAR_S 4u
+
+/* A set of 2-bit packed sequences (Sequence.java:10-13,31-41: A=0 C=1 T=2 G=3, 4 bases/byte, LSB first).
+ * Sequence k occupies ceil(len[k]/4) bytes starting at packed + off[k].
+ * nmask (optional, NULL = no N anywhere): 1 bit per base, LSB first, sequence k at nmask + nmask_off[k]. */
+typedef struct {
+  const uint8_t*  packed;
+  const uint32_t* off;
+  const uint16_t* len;
+  const uint8_t*  nmask;
+  const uint32_t* nmask_off;
+  uint32_t        count;
+  uint32_t        packed_bytes;   /* total bytes readable at packed */
+  uint32_t        nmask_bytes;    /* total bytes readable at nmask (0 if NULL) */
+} ubu_sw_seqs;
+
+typedef struct ubu_sw_handle ubu_sw_handle;
+
+/* Stands in for `new Aligner(reference, numThreads)` (Aligner.java:13-16): one handle per GPU.
+ * params == NULL -> SPEC defaults. slots = depth of the H2D/compute/D2H pipeline (1..4; 0 -> 2). */
+int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_handle** out);
+void ubu_sw_destroy(ubu_sw_handle* h);
+
+/* Stands in for Aligner.shortAlign / Aligner.align (Aligner.java:18-22,46-56): align read k against
+ * window pair_ref_idx[k] (NULL = identity, then reads->count must equal windows->count).
+ * out[k] and the CIGAR slice it names describe read k: results are in INPUT order.
+ * Synchronous: host->device copies, all kernels and device->host copies complete before return. */
+int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows,
+                       const uint32_t* pair_ref_idx, ubu_sw_result* out,
+                       uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);
+
+/* Pipelined form of the same call: submit() plans the batch, enqueues copies and kernels on the next
+ * free slot's stream and returns a ticket; wait() blocks until that batch's results are in `out`.
+ * All caller buffers must stay valid until wait() returns; use ubu_sw_host_alloc for overlap. */
+int ubu_sw_submit(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows,
+                  const uint32_t* pair_ref_idx, ubu_sw_result* out,
+                  uint32_t* cigar_pool, size_t cigar_pool_cap, int* ticket);
+int ubu_sw_wait(ubu_sw_handle* h, int ticket, size_t* cigar_pool_used);
+
+/* Staged form used by bench.py's device-resident timing (`value`): stage() = plan + H2D into slot
+ * `slot`; run() = enqueue every kernel of the path on the slot's stream (inputs and results stay in HBM);
+ * sync() = wait for the slot's stream; fetch() = D2H of results + CIGARs of the last run(). */
+int ubu_sw_stage(ubu_sw_handle* h, int slot, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows,
+                 const uint32_t* pair_ref_idx);
+int ubu_sw_run(ubu_sw_handle* h, int slot);
+int ubu_sw_sync(ubu_sw_handle* h, int slot);
+int ubu_sw_fetch(ubu_sw_handle* h, int slot, ubu_sw_result* out,
+                 uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);
+/* Device time in ms of the last run() on the slot (CUDA events on the slot's stream): [0] whole run,
+ * [1] forward (score) kernels, [2] traceback + CIGAR kernels. Valid after sync(). */
+int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]);
+/* Number of kernel launches issued by the last run() on the slot. */
+int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot);
+
+/* Pinned host memory for the caller's buffers (cudaHostAlloc); plain malloc'd buffers also work, slower. */
+void* ubu_sw_host_alloc(size_t bytes);
+void  ubu_sw_host_free(void* p);
+
+/* Host-side helpers on the reference's sequence conventions (no GPU needed). */
+/* text -> 2-bit codes + N bit-plane (Sequence.java:31-41; non-ACGT -> N, case-folded). */
+void ubu_sw_pack(const char* text, size_t n, uint8_t* packed, uint8_t* nmask, int* has_n);
+/* ReverseComplementor.java:38-62: A<->T, C<->G, every other byte unchanged. */
+void ubu_sw_revcomp(const char* in, size_t n, char* out);
+/* BAM-encoded ops -> "76M" style text; returns chars written (excluding NUL), "*" for n == 0. */
+int  ubu_sw_cigar_string(const uint32_t* ops, uint32_t n, char* buf, size_t cap);
+
+int          ubu_sw_device_count(void);
+unsigned     ubu_sw_version(void);
+const char*  ubu_sw_strerror(int status);
+const char*  ubu_sw_last_error(ubu_sw_handle* h);   /* text of the last CUDA failure on this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBU_SW_H */

@@ -1,0 +1,68 @@
+// sw_common.cuh -- shared device-side types for the SPEC.md Smith-Waterman path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ubu_sw.h"
+
+namespace ubu {
+
+// Device view of a ubu_sw_seqs (include/ubu_sw.h): 2-bit codes A=0 C=1 T=2 G=3, LSB first
+// (reference convention, Sequence.java:10-13,31-41) + optional N bit-plane.
+struct DevSeqs {
+  const uint8_t* packed;
+  const uint32_t* off;
+  const uint16_t* len;
+  const uint8_t* nmask;        // nullptr = no N anywhere in this set
+  const uint32_t* nmask_off;
+};
+
+struct Scoring { int match, mismatch, gap_open, gap_ext; };
+
+// Output of the forward (score) pass, input of the traceback pass. 16 bytes.
+// The end column is exact; the end row is known to lie in [i_lo, i_hi] (the K rows one
+// lane owns); the traceback pass resolves it (SPEC.md section 4: smallest j, then smallest i).
+struct FwdOut { int32_t score, je, i_lo, i_hi; };
+
+__device__ __forceinline__ uint32_t base2(const uint8_t* __restrict__ p, uint32_t k) {
+  return (uint32_t)(p[k >> 2] >> ((k & 3u) * 2u)) & 3u;
+}
+__device__ __forceinline__ uint32_t nbit(const uint8_t* __restrict__ m, uint32_t k) {
+  return (uint32_t)(m[k >> 3] >> (k & 7u)) & 1u;
+}
+__device__ __forceinline__ uint32_t pack16x2(int v) {
+  return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16);
+}
+
+// prmt.b32 in its default mode: selector nibble bit 3 set = replicate the selected byte's sign bit.
+// (Inline PTX rather than __byte_perm, whose documented contract only covers selector bits 2:0.)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s)); return d;
+}
+
+// Packed max with "old value kept" predicates: returns max(a,b) per half, keep_* = (a >= b).
+// Same PTX idiom as the toolkit's __vibmax_s16x2 (which ptxas turns into one VIMNMX.S16x2 with two
+// predicate outputs), but with an early-clobber output: the toolkit version lets the result alias
+// input a, and `best = __vibmax_s16x2(best, ...)` then compares the result with itself.
+__device__ __forceinline__ uint32_t vmax2_keep(uint32_t a, uint32_t b, bool& keep_hi, bool& keep_lo) {
+  uint32_t val, ph, pl;
+  asm("{.reg .pred pu, pv;\n\t"
+      ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+      "max.s16x2 %0, %3, %4;\n\t"
+      "mov.b32 {rs0, rs1}, %0;\n\t"
+      "mov.b32 {rs2, rs3}, %3;\n\t"
+      "setp.eq.s16 pv, rs0, rs2;\n\t"
+      "setp.eq.s16 pu, rs1, rs3;\n\t"
+      "selp.b32 %1, 1, 0, pu;\n\t"
+      "selp.b32 %2, 1, 0, pv;}"
+      : "=&r"(val), "=r"(ph), "=r"(pl) : "r"(a), "r"(b));
+  keep_hi = ph != 0u; keep_lo = pl != 0u;
+  return val;
+}
+
+// Gap bound of SPEC.md section 7: max gap bases on a path of score S ending in row <= i.
+__host__ __device__ __forceinline__ int gap_bound(const Scoring& sc, int i, int S) {
+  const int num = sc.match * i - sc.gap_open - S;
+  return num > 0 ? num / sc.gap_ext : 0;
+}
+
+}  // namespace ubu

@@ -1,0 +1,186 @@
+// sw_fwd16.cuh -- forward (score + end cell) pass, packed 16-bit lanes, sm_100a.
+//
+// Layout of the work: a GROUP of G consecutive lanes of one warp aligns a PAIR of tasks at once,
+// task A in the low and task B in the high 16-bit half of every register (inter-task SIMD).
+// Lane g owns K consecutive read rows [g*K, g*K+K) of both tasks in registers; the group sweeps
+// the window as a systolic wavefront: at step s lane g updates its K cells of column s-g, then
+// hands its bottom H (as H-oe) and the F entering the row below to lane g+1 with two warp shuffles.
+//
+// Per packed cell (two DP cells) the ALU work is:
+//     PRMT              substitution score of (A,B) from the per-row byte profiles      [ALU]
+//     VIADDMNMX.S16x2   E = max(E - ext, Hleft - oe)                                    [ALU]
+//     VIADD.16x2        t = Hdiag - oe + (s + oe)                                       [second int pipe]
+//     VIMNMX3.S16x2.RELU H = max(0, t, E, F)                                            [ALU]
+//     VIADD.16x2        Hoe = H - oe     (feeds E of the next column, F of the next row, diag)
+//     VIADDMNMX.S16x2   F = max(F - ext, Hoe)                                           [ALU]
+//     VIMNMX3.S16x2     running column max, one op per two rows                         [ALU]
+// which is the 7-op cell of SURVEY.md section 8d with the score lookup added and the running
+// max halved. No shared-memory traffic in the cell loop except one selector load per lane per step.
+//
+// Substitution scores without a table lookup: row r of lane g keeps ONE register per task holding
+// four int8 scores (vs A,C,T,G, each pre-biased by +oe); the window base of the current column is
+// turned (once per pair, in the prologue) into a 16-bit PRMT selector kept in shared memory, so a
+// single PRMT yields the sign-extended (scoreB:scoreA) pair. Padding rows use -128 bytes, padding
+// columns use the sign-replicate selector (score 0 or -1 after bias => H stays below every real
+// cell), so ragged pairs need no masks. N in the read = a row of (0+oe) bytes; N in the window needs
+// one extra LOP3 per cell and is compiled only into the HAS_N variant.
+//
+// Arg-max: each lane keeps the running packed best and the step at which it first strictly
+// improved; the group reduction orders candidates by (score, smaller column, smaller lane), which
+// is exactly SPEC.md section 4 at lane granularity. The row inside the winning lane's K rows is
+// resolved by the traceback pass.
+#pragma once
+#include "sw_common.cuh"
+#include <type_traits>
+
+namespace ubu {
+
+template <bool HAS_N> struct SelType { using type = uint16_t; };
+template <> struct SelType<true> { using type = uint32_t; };
+
+template <int G, int K, bool HAS_N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
+                const uint32_t* __restrict__ order, uint32_t n_slots, Scoring sc,
+                FwdOut* __restrict__ out, int sel_stride) {
+  static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide the warp");
+  constexpr int GP = THREADS / G;
+  using SelT = typename SelType<HAS_N>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelT* sel_all = reinterpret_cast<SelT*>(smem_raw);
+  __shared__ int s_wmax;
+
+  const int tid = threadIdx.x;
+  const int grp = tid / G, g = tid % G;
+  if (tid == 0) s_wmax = 0;
+
+  // ---- the pair of tasks of this group --------------------------------------------------
+  const uint32_t slotA = 2u * (blockIdx.x * GP + grp), slotB = slotA + 1u;
+  const uint32_t tA = slotA < n_slots ? order[slotA] : 0xFFFFFFFFu;
+  const uint32_t tB = slotB < n_slots ? order[slotB] : 0xFFFFFFFFu;
+  int LA = 0, WA = 0, LB = 0, WB = 0;
+  const uint8_t *qA = nullptr, *qB = nullptr, *rA = nullptr, *rB = nullptr;
+  const uint8_t *qnA = nullptr, *qnB = nullptr, *rnA = nullptr, *rnB = nullptr;
+  if (tA != 0xFFFFFFFFu) {
+    const uint32_t ri = ref_idx ? ref_idx[tA] : tA;
+    LA = reads.len[tA]; qA = reads.packed + reads.off[tA];
+    WA = wins.len[ri];  rA = wins.packed + wins.off[ri];
+    if (reads.nmask) qnA = reads.nmask + reads.nmask_off[tA];
+    if (HAS_N && wins.nmask) rnA = wins.nmask + wins.nmask_off[ri];
+  }
+  if (tB != 0xFFFFFFFFu) {
+    const uint32_t ri = ref_idx ? ref_idx[tB] : tB;
+    LB = reads.len[tB]; qB = reads.packed + reads.off[tB];
+    WB = wins.len[ri];  rB = wins.packed + wins.off[ri];
+    if (reads.nmask) qnB = reads.nmask + reads.nmask_off[tB];
+    if (HAS_N && wins.nmask) rnB = wins.nmask + wins.nmask_off[ri];
+  }
+
+  // ---- per-row byte profiles (registers) ------------------------------------------------
+  const int oe = sc.gap_open + sc.gap_ext;
+  const uint32_t mmb = (uint32_t)(sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(sc.match + oe) & 0xFFu;
+  const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
+  uint32_t profA[K], profB[K];
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int row = g * K + r;
+    uint32_t pa = 0x80808080u, pb = 0x80808080u;          // padding row: -128 against every base
+    if (row < LA) { pa = MM4 ^ (MX << (8u * base2(qA, row))); if (qnA && nbit(qnA, row)) pa = N4; }
+    if (row < LB) { pb = MM4 ^ (MX << (8u * base2(qB, row))); if (qnB && nbit(qnB, row)) pb = N4; }
+    profA[r] = pa; profB[r] = pb;
+  }
+
+  // ---- per-column PRMT selectors (shared memory), index = column + G ----------------------
+  SelT* sel = sel_all + (size_t)grp * sel_stride;
+  for (int idx = g; idx < sel_stride; idx += G) {
+    const int c = idx - G;
+    uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;             // padding column: sign-replicate selectors
+    if (c >= 0 && c < WA) {
+      const uint32_t b = base2(rA, c); lo = b | ((b | 8u) << 4);
+      if (HAS_N && rnA && nbit(rnA, c)) nf |= 0x00800000u;
+    }
+    if (c >= 0 && c < WB) {
+      const uint32_t b = base2(rB, c) + 4u; hi = b | ((b | 8u) << 4);
+      if (HAS_N && rnB && nbit(rnB, c)) nf |= 0x80000000u;
+    }
+    sel[idx] = (SelT)(lo | (hi << 8) | nf);
+  }
+  __syncthreads();
+  if (g == 0) atomicMax(&s_wmax, max(WA, WB));
+  __syncthreads();
+  const int nsteps = s_wmax > 0 ? s_wmax + G - 1 : 0;
+
+  // ---- systolic sweep ---------------------------------------------------------------------
+  const uint32_t NEG_OE = pack16x2(-oe), NEG_EXT = pack16x2(-sc.gap_ext), POS_OE = pack16x2(oe);
+  uint32_t Hoe[K], E[K];
+#pragma unroll
+  for (int r = 0; r < K; ++r) { Hoe[r] = NEG_OE; E[r] = NEG_OE; }
+  uint32_t hoe_bot = NEG_OE, f_bot = NEG_OE, hoe_up_prev = NEG_OE;
+  uint32_t best = 0u; int stepA = 0, stepB = 0;
+  const SelT* selp = sel + (G - g);                       // selp[s] = selector of column s - g
+
+#pragma unroll 1
+  for (int s = 0; s < nsteps; ++s) {
+    const uint32_t selv = selp[s];
+    uint32_t up = __shfl_up_sync(0xffffffffu, hoe_bot, 1, G);
+    uint32_t F = __shfl_up_sync(0xffffffffu, f_bot, 1, G);
+    if (g == 0) { up = NEG_OE; F = NEG_OE; }              // row 0: H[0][j] = 0, F[1][j] = -oe
+    uint32_t hd = hoe_up_prev;                            // H[top-1][j-1] - oe
+    hoe_up_prev = up;
+    uint32_t isn = 0u;
+    if (HAS_N) isn = prmt(selv, 0u, 0xBBAAu);      // 0xFFFF per half whose window base is N
+    uint32_t colmax = 0u, hprev = 0u;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      uint32_t sp = prmt(profA[r], profB[r], selv & 0xFFFFu);       // (s+oe) of B : A
+      if (HAS_N) sp = (sp & ~isn) | (POS_OE & isn);                          // window N scores 0
+      E[r] = __viaddmax_s16x2(E[r], NEG_EXT, Hoe[r]);                        // E[i][j]
+      const uint32_t t = __vadd2(hd, sp);                                    // H[i-1][j-1] + s
+      hd = Hoe[r];
+      const uint32_t h = __vimax3_s16x2_relu(t, E[r], F);                    // H[i][j]
+      Hoe[r] = __vadd2(h, NEG_OE);
+      F = __viaddmax_s16x2(F, NEG_EXT, Hoe[r]);                              // F[i+1][j]
+      if (r & 1) colmax = __vimax3_s16x2(colmax, hprev, h); else hprev = h;
+    }
+    if (K & 1) colmax = __vmaxs2(colmax, hprev);
+    hoe_bot = Hoe[K - 1]; f_bot = F;
+    bool keep_hi, keep_lo;                                                   // true = old best >= column max
+    best = vmax2_keep(best, colmax, keep_hi, keep_lo);
+    if (!keep_lo) stepA = s;
+    if (!keep_hi) stepB = s;
+  }
+
+  // ---- group arg-max: (score, smaller column, smaller lane) -------------------------------
+  const int scA = (int)(int16_t)(best & 0xFFFFu), scB = (int)(int16_t)(best >> 16);
+  unsigned long long keyA = 0ull, keyB = 0ull;
+  if (scA > 0) keyA = ((unsigned long long)scA << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepA - g + 1)) << 8) | (unsigned long long)(31 - g);
+  if (scB > 0) keyB = ((unsigned long long)scB << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepB - g + 1)) << 8) | (unsigned long long)(31 - g);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const unsigned long long oa = __shfl_xor_sync(0xffffffffu, keyA, o, G);
+    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, keyB, o, G);
+    keyA = oa > keyA ? oa : keyA; keyB = ob > keyB ? ob : keyB;
+  }
+  if (g == 0) {
+    if (tA != 0xFFFFFFFFu) {
+      FwdOut o = {0, 0, 0, 0};
+      if (keyA) {
+        const int lane = 31 - (int)(keyA & 0xFFu);
+        o.score = (int)(keyA >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyA >> 8) & 0xFFFFu));
+        o.i_lo = lane * K + 1; o.i_hi = min(LA, lane * K + K);
+      }
+      out[tA] = o;
+    }
+    if (tB != 0xFFFFFFFFu) {
+      FwdOut o = {0, 0, 0, 0};
+      if (keyB) {
+        const int lane = 31 - (int)(keyB & 0xFFu);
+        o.score = (int)(keyB >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyB >> 8) & 0xFFFFu));
+        o.i_lo = lane * K + 1; o.i_hi = min(LB, lane * K + K);
+      }
+      out[tB] = o;
+    }
+  }
+}
+
+}  // namespace ubu

@@ -1,0 +1,575 @@
+// ubu_sw.cu -- host side of libubu_sw.so: the C ABI of include/ubu_sw.h, the per-batch plan
+// (length classes, pairing, window-length ordering), the stream pipeline and the kernel launches.
+// Product path: there is NO CPU alignment code in this library and no fallback; every entry point
+// that needs the GPU fails with UBU_SW_ERR_NO_DEVICE / UBU_SW_ERR_CUDA when it is not there.
+#include "sw_fwd16.cuh"
+#include "sw_tb.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ubu;
+
+namespace {
+
+// ---- length classes of the packed 16-bit forward kernel: rows capacity = G*K -------------------
+struct FwdCfg { int lmax, G, K; };
+constexpr int FWD_THREADS = 64;
+#define UBU_FWD_CFGS(X) X(0, 32, 8, 4) X(1, 48, 8, 6) X(2, 64, 8, 8) X(3, 80, 8, 10) X(4, 96, 8, 12) X(5, 104, 8, 13) \
+  X(6, 128, 8, 16) X(7, 160, 16, 10) X(8, 192, 16, 12) X(9, 208, 16, 13) X(10, 256, 16, 16)
+#define X(i, l, g, k) {l, g, k},
+const FwdCfg kFwdCfgs[] = {UBU_FWD_CFGS(X)};
+#undef X
+constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
+constexpr size_t kMaxDynSmem = 200 * 1024;
+
+constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 4;
+constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; };
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  DevBuf<uint8_t> d_rp, d_rn, d_wp, d_wn;
+  DevBuf<uint32_t> d_roff, d_rnoff, d_woff, d_wnoff, d_idx, d_order, d_lists, d_cig;
+  DevBuf<uint16_t> d_rlen, d_wlen;
+  DevBuf<FwdOut> d_fwd;
+  DevBuf<ubu_sw_result> d_res;
+  DevBuf<unsigned int> d_ctr;            // [0..2] class counts, [3] cigar cursor, [4] error flags
+  DevBuf<unsigned long long> d_dir;      // direction scratch of the register-band traceback kernels
+  DevBuf<unsigned char> d_wide;          // scratch of the wide-band traceback kernel
+  PinBuf<uint32_t> h_order;
+  PinBuf<unsigned int> h_ctr;
+  std::vector<FwdLaunch> launches;
+  std::vector<uint32_t> tmp_keys, tmp_idx;
+  // staged batch
+  bool staged = false, ran = false, pending = false;
+  uint32_t n_tasks = 0, n_slots = 0;
+  bool any_n = false, have_idx = false, reads_n = false, wins_n = false;
+  int lmax = 0, bw_cap = 0;
+  unsigned int cig_cap = 0;
+  int n_launches = 0;
+  // submit()/wait() bookkeeping
+  ubu_sw_result* out = nullptr; uint32_t* pool = nullptr; size_t pool_cap = 0;
+};
+
+}  // namespace
+
+struct ubu_sw_handle {
+  int device = 0, n_slots = 2, sm_count = 148;
+  Scoring sc{1, -3, 5, 2};
+  Slot slots[4];
+  std::string last_error;
+  int next_slot = 0;
+};
+
+namespace {
+
+int fail_cuda(ubu_sw_handle* h, cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  if (h) h->last_error = buf;
+  return UBU_SW_ERR_CUDA;
+}
+#define CU(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda((h), e__, #call); } while (0)
+
+int cfg_of_len(int L) {
+  for (int c = 0; c < kNumCfgs; ++c) if (L <= kFwdCfgs[c].lmax) return c;
+  return -1;
+}
+
+int sel_stride_for(int wmax, int G) { return ((wmax + 2 * G + 63) / 64) * 64 + G; }
+
+size_t fwd_smem_bytes(int cfg, bool has_n, int wmax) {
+  const FwdCfg& c = kFwdCfgs[cfg];
+  return (size_t)(FWD_THREADS / c.G) * (size_t)sel_stride_for(wmax, c.G) * (has_n ? 4u : 2u);
+}
+
+template <int G, int K, bool HAS_N>
+cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
+                         const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+  constexpr int GP = FWD_THREADS / G;
+  const int stride = sel_stride_for(L.wmax, G);
+  const size_t smem = (size_t)GP * stride * (HAS_N ? 4u : 2u);
+  auto kern = sw_fwd16_kernel<G, K, HAS_N, FWD_THREADS>;
+  if (smem > 48 * 1024) {      // per device, so set on every large launch (cheap)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+  }
+  const uint32_t pairs = L.n_slots / 2;
+  const uint32_t grid = (pairs + GP - 1) / GP;
+  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, order + L.begin, L.n_slots, sc, out, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
+                       const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+  switch (L.cfg * 2 + (L.has_n ? 1 : 0)) {
+#define X(i, l, g, k) \
+    case i * 2: return launch_fwd_t<g, k, false>(L, reads, wins, idx, order, sc, out, st); \
+    case i * 2 + 1: return launch_fwd_t<g, k, true>(L, reads, wins, idx, order, sc, out, st);
+    UBU_FWD_CFGS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+bool params_ok(const ubu_sw_params& p) {
+  return p.match >= 1 && p.match <= 31 && p.mismatch <= 0 && p.mismatch >= -64 && p.gap_open >= 0 && p.gap_open <= 63 &&
+         p.gap_ext >= 1 && p.gap_ext <= 31;
+}
+
+int validate_seqs(const ubu_sw_seqs* s) {
+  if (!s) return UBU_SW_ERR_ARG;
+  if (s->count && (!s->off || !s->len)) return UBU_SW_ERR_ARG;
+  if (s->count && s->packed_bytes && !s->packed) return UBU_SW_ERR_ARG;
+  if (s->nmask && !s->nmask_off) return UBU_SW_ERR_ARG;
+  return UBU_SW_OK;
+}
+
+// ---- plan: class per task, order by (class, window length), pad classes to pairs ------------------
+int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx) {
+  const uint32_t n = reads->count;
+  std::vector<uint8_t> win_has_n;
+  if (wins->nmask) {
+    win_has_n.assign(wins->count, 0);
+    for (uint32_t w = 0; w < wins->count; ++w) {
+      const uint32_t nb = ((uint32_t)wins->len[w] + 7u) / 8u;
+      if ((uint64_t)wins->nmask_off[w] + nb > wins->nmask_bytes) return UBU_SW_ERR_ARG;
+      const uint8_t* m = wins->nmask + wins->nmask_off[w];
+      uint8_t any = 0;
+      for (uint32_t k = 0; k < nb; ++k) any |= m[k];
+      win_has_n[w] = any ? 1 : 0;
+    }
+  }
+  for (uint32_t w = 0; w < wins->count; ++w)
+    if ((uint64_t)wins->off[w] + ((uint32_t)wins->len[w] + 3u) / 4u > wins->packed_bytes) return UBU_SW_ERR_ARG;
+
+  constexpr int NB = kNumCfgs * 2;
+  uint32_t cnt[NB] = {0};
+  int wmin[NB], wmaxv[NB];
+  for (int b = 0; b < NB; ++b) { wmin[b] = 1 << 30; wmaxv[b] = 0; }
+  s.tmp_keys.resize(n);
+  int lmax = 0;
+  for (uint32_t t = 0; t < n; ++t) {
+    const int L = reads->len[t];
+    const uint32_t ri = idx ? idx[t] : t;
+    if (ri >= wins->count) return UBU_SW_ERR_ARG;
+    if ((uint64_t)reads->off[t] + ((uint32_t)L + 3u) / 4u > reads->packed_bytes) return UBU_SW_ERR_ARG;
+    if (reads->nmask && (uint64_t)reads->nmask_off[t] + ((uint32_t)L + 7u) / 8u > reads->nmask_bytes) return UBU_SW_ERR_ARG;
+    const int c = cfg_of_len(L);
+    if (c < 0) return UBU_SW_ERR_TOO_LONG;
+    const int W = wins->len[ri];
+    const int b = c * 2 + (wins->nmask && win_has_n[ri] ? 1 : 0);
+    ++cnt[b];
+    wmin[b] = std::min(wmin[b], W); wmaxv[b] = std::max(wmaxv[b], W);
+    lmax = std::max(lmax, L);
+    s.tmp_keys[t] = ((uint32_t)b << 16) | (uint32_t)W;
+  }
+  s.lmax = lmax;
+
+  // bucket starts (each bucket padded to an even number of slots)
+  uint32_t start[NB + 1]; start[0] = 0;
+  for (int b = 0; b < NB; ++b) start[b + 1] = start[b] + ((cnt[b] + 1u) & ~1u);
+  s.n_slots = start[NB];
+  if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots, 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
+  uint32_t* order = s.h_order.p;
+  uint32_t fill[NB];
+  for (int b = 0; b < NB; ++b) fill[b] = start[b];
+  for (uint32_t t = 0; t < n; ++t) order[fill[s.tmp_keys[t] >> 16]++] = t;
+  for (int b = 0; b < NB; ++b) if (cnt[b] & 1u) order[fill[b]] = 0xFFFFFFFFu;
+
+  // inside a bucket, order by window length when it varies (so a pair / a warp sweeps similar widths)
+  s.launches.clear();
+  for (int b = 0; b < NB; ++b) {
+    if (!cnt[b]) continue;
+    uint32_t* lo = order + start[b];
+    if (wmin[b] != wmaxv[b]) {
+      std::stable_sort(lo, lo + cnt[b], [&](uint32_t x, uint32_t y) { return (s.tmp_keys[x] & 0xFFFFu) < (s.tmp_keys[y] & 0xFFFFu); });
+    }
+    const int cfg = b / 2; const bool has_n = b & 1;
+    if (fwd_smem_bytes(cfg, has_n, wmaxv[b]) > kMaxDynSmem) return UBU_SW_ERR_TOO_LONG;
+    // split a bucket whose widths vary a lot so that short windows do not pay the long ones' shared memory
+    uint32_t beg = 0; const uint32_t total = (cnt[b] + 1u) & ~1u;
+    while (beg < total) {
+      uint32_t end = total;
+      if (wmin[b] != wmaxv[b]) {
+        const int w0 = (int)(s.tmp_keys[lo[beg]] & 0xFFFFu);
+        const int limit = std::max(w0 * 2, 512);
+        uint32_t e = beg;
+        while (e < cnt[b] && (int)(s.tmp_keys[lo[e]] & 0xFFFFu) <= limit) ++e;
+        e = (e + 1u) & ~1u;                 // keep pairs intact
+        if (e > total) e = total;
+        if (e < total && e > beg) end = e;
+      }
+      int wm = 0;
+      for (uint32_t k = beg; k < end && k < cnt[b]; ++k) wm = std::max(wm, (int)(s.tmp_keys[lo[k]] & 0xFFFFu));
+      s.launches.push_back(FwdLaunch{cfg, has_n, start[b] + beg, end - beg, wm});
+      beg = end;
+    }
+  }
+  return UBU_SW_OK;
+}
+
+int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx) {
+  int rc = validate_seqs(reads); if (rc) return rc;
+  rc = validate_seqs(wins); if (rc) return rc;
+  if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
+  s.staged = false; s.ran = false;
+  s.n_tasks = reads->count;
+  s.have_idx = idx != nullptr;
+  s.reads_n = reads->nmask != nullptr; s.wins_n = wins->nmask != nullptr;
+  s.any_n = s.reads_n || s.wins_n;
+  if (s.n_tasks == 0) { s.n_slots = 0; s.launches.clear(); s.staged = true; return UBU_SW_OK; }
+  rc = plan_batch(h, s, reads, wins, idx); if (rc) return rc;
+
+  const uint32_t n = s.n_tasks, nw = wins->count;
+  CU(h, s.d_rp.reserve(reads->packed_bytes + 16)); CU(h, s.d_roff.reserve(n)); CU(h, s.d_rlen.reserve(n));
+  CU(h, s.d_wp.reserve(wins->packed_bytes + 16)); CU(h, s.d_woff.reserve(nw)); CU(h, s.d_wlen.reserve(nw));
+  if (s.reads_n) { CU(h, s.d_rn.reserve(reads->nmask_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
+  if (s.wins_n) { CU(h, s.d_wn.reserve(wins->nmask_bytes + 16)); CU(h, s.d_wnoff.reserve(nw)); }
+  if (idx) CU(h, s.d_idx.reserve(n));
+  CU(h, s.d_order.reserve(s.n_slots)); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
+  CU(h, s.d_fwd.reserve(n)); CU(h, s.d_res.reserve(n));
+  CU(h, s.d_ctr.reserve(8)); CU(h, s.h_ctr.reserve(8));
+  if (s.cig_cap < 6u * n + 4096u) { s.cig_cap = 6u * n + 4096u; }
+  CU(h, s.d_cig.reserve(s.cig_cap));
+  // traceback scratch
+  const int max_rows = std::max(s.lmax, 1);
+  const size_t tb_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
+  CU(h, s.d_dir.reserve(tb_threads * (size_t)max_rows * 2));          // NW = 2 is the widest register class
+  {
+    int kmax = 16;
+    const int gbmax = gap_bound(h->sc, max_rows, 1);
+    s.bw_cap = std::min(kmax + 2 * gbmax + 1, max_rows + 65535);
+    const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
+    CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
+  }
+
+  cudaStream_t st = s.stream;
+  CU(h, cudaMemcpyAsync(s.d_rp.p, reads->packed, reads->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_roff.p, reads->off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_rlen.p, reads->len, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_wp.p, wins->packed, wins->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_woff.p, wins->off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_wlen.p, wins->len, sizeof(uint16_t) * nw, cudaMemcpyHostToDevice, st));
+  if (s.reads_n) {
+    CU(h, cudaMemcpyAsync(s.d_rn.p, reads->nmask, reads->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.d_rnoff.p, reads->nmask_off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  }
+  if (s.wins_n) {
+    CU(h, cudaMemcpyAsync(s.d_wn.p, wins->nmask, wins->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.d_wnoff.p, wins->nmask_off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
+  }
+  if (idx) CU(h, cudaMemcpyAsync(s.d_idx.p, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_order.p, s.h_order.p, sizeof(uint32_t) * s.n_slots, cudaMemcpyHostToDevice, st));
+  s.staged = true;
+  return UBU_SW_OK;
+}
+
+int do_run(ubu_sw_handle* h, Slot& s) {
+  if (!s.staged) return UBU_SW_ERR_ARG;
+  cudaStream_t st = s.stream;
+  s.n_launches = 0;
+  CU(h, cudaEventRecord(s.ev[0], st));
+  if (s.n_tasks == 0) { CU(h, cudaEventRecord(s.ev[1], st)); CU(h, cudaEventRecord(s.ev[2], st)); s.ran = true; return UBU_SW_OK; }
+  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, 8 * sizeof(unsigned int), st));
+  DevSeqs reads{s.d_rp.p, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
+  DevSeqs wins{s.d_wp.p, s.d_woff.p, s.d_wlen.p, s.wins_n ? s.d_wn.p : nullptr, s.wins_n ? s.d_wnoff.p : nullptr};
+  const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
+  for (const FwdLaunch& L : s.launches) {
+    CU(h, launch_fwd(L, reads, wins, idx, s.d_order.p, h->sc, s.d_fwd.p, st));
+    ++s.n_launches;
+  }
+  CU(h, cudaEventRecord(s.ev[1], st));
+
+  TbArgs a;
+  a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
+  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 3; a.err_flag = s.d_ctr.p + 4;
+  const int max_rows = std::max(s.lmax, 1);
+  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(s.d_order.p, s.n_slots, s.d_fwd.p, h->sc, s.d_res.p, s.d_lists.p, s.d_ctr.p);
+  CU(h, cudaGetLastError()); ++s.n_launches;
+  const int tb_grid = h->sm_count * TB_GRID_PER_SM;
+  if (s.any_n) {
+    tb_band_kernel<16, true, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0, s.d_dir.p, max_rows);
+    CU(h, cudaGetLastError());
+    tb_band_kernel<32, true, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p + s.n_slots, s.d_ctr.p + 1, s.d_dir.p, max_rows);
+    CU(h, cudaGetLastError());
+  } else {
+    tb_band_kernel<16, false, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0, s.d_dir.p, max_rows);
+    CU(h, cudaGetLastError());
+    tb_band_kernel<32, false, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p + s.n_slots, s.d_ctr.p + 1, s.d_dir.p, max_rows);
+    CU(h, cudaGetLastError());
+  }
+  tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, st>>>(a, s.d_lists.p + 2 * (size_t)s.n_slots, s.d_ctr.p + 2,
+                                                                     s.d_wide.p, max_rows, s.bw_cap);
+  CU(h, cudaGetLastError());
+  s.n_launches += 3;
+  CU(h, cudaEventRecord(s.ev[2], st));
+  s.ran = true;
+  return UBU_SW_OK;
+}
+
+int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size_t pool_cap, size_t* used) {
+  if (!s.ran) return UBU_SW_ERR_ARG;
+  if (used) *used = 0;
+  if (s.n_tasks == 0) return UBU_SW_OK;
+  if (!out) return UBU_SW_ERR_ARG;
+  cudaStream_t st = s.stream;
+  for (int attempt = 0;; ++attempt) {
+    CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    const unsigned int need = s.h_ctr.p[3], err = s.h_ctr.p[4];
+    if (err & 2u) { h->last_error = "internal: traceback left its band (please report)"; return UBU_SW_ERR_CUDA; }
+    if (err & 1u) {                    // device CIGAR pool was too small: grow it and redo the device work once
+      if (attempt) { h->last_error = "internal: CIGAR pool overflow after regrow"; return UBU_SW_ERR_CUDA; }
+      s.cig_cap = need + 4096u;
+      CU(h, s.d_cig.reserve(s.cig_cap));
+      int rc = do_run(h, s); if (rc) return rc;
+      continue;
+    }
+    if (used) *used = need;
+    if (need > pool_cap || (need && !pool)) return UBU_SW_ERR_CIGAR_POOL;
+    CU(h, cudaMemcpyAsync(out, s.d_res.p, sizeof(ubu_sw_result) * s.n_tasks, cudaMemcpyDeviceToHost, st));
+    if (need) CU(h, cudaMemcpyAsync(pool, s.d_cig.p, sizeof(uint32_t) * need, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return UBU_SW_OK;
+  }
+}
+
+}  // namespace
+
+// ================================= C ABI ========================================================
+extern "C" {
+
+int ubu_sw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+unsigned ubu_sw_version(void) { return UBU_SW_VERSION; }
+
+const char* ubu_sw_strerror(int status) {
+  switch (status) {
+    case UBU_SW_OK: return "ok";
+    case UBU_SW_ERR_ARG: return "invalid argument";
+    case UBU_SW_ERR_CUDA: return "CUDA failure";
+    case UBU_SW_ERR_CIGAR_POOL: return "CIGAR pool too small";
+    case UBU_SW_ERR_TOO_LONG: return "read or window too long for this build";
+    case UBU_SW_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required)";
+    case UBU_SW_ERR_BUSY: return "no free pipeline slot / ticket not pending";
+    case UBU_SW_ERR_NOMEM: return "out of host memory";
+    default: return "unknown status";
+  }
+}
+
+const char* ubu_sw_last_error(ubu_sw_handle* h) { return h ? h->last_error.c_str() : ""; }
+
+int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_handle** out) {
+  if (!out) return UBU_SW_ERR_ARG;
+  *out = nullptr;
+  ubu_sw_params p = params ? *params : ubu_sw_params{1, -3, 5, 2};
+  if (!params_ok(p)) return UBU_SW_ERR_ARG;
+  if (slots == 0) slots = 2;
+  if (slots < 1 || slots > 4) return UBU_SW_ERR_ARG;
+  int ndev = ubu_sw_device_count();
+  if (device < 0 || device >= ndev) return UBU_SW_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return UBU_SW_ERR_NO_DEVICE; }
+  if (prop.major != 10) return UBU_SW_ERR_NO_DEVICE;            // sm_100a code only: no other code path exists
+  ubu_sw_handle* h = new (std::nothrow) ubu_sw_handle();
+  if (!h) return UBU_SW_ERR_NOMEM;
+  h->device = device; h->n_slots = slots; h->sm_count = prop.multiProcessorCount;
+  h->sc = Scoring{p.match, p.mismatch, p.gap_open, p.gap_ext};
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return UBU_SW_ERR_CUDA; }
+  for (int i = 0; i < slots; ++i) {
+    if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    for (int e = 0; e < 3; ++e)
+      if (cudaEventCreate(&h->slots[i].ev[e]) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+  }
+  *out = h;
+  return UBU_SW_OK;
+}
+
+void ubu_sw_destroy(ubu_sw_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 4; ++i) {
+    Slot& s = h->slots[i];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
+    s.d_roff.release(); s.d_rnoff.release(); s.d_woff.release(); s.d_wnoff.release(); s.d_idx.release();
+    s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
+    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_dir.release(); s.d_wide.release();
+    s.h_order.release(); s.h_ctr.release();
+    for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  delete h;
+}
+
+int ubu_sw_stage(ubu_sw_handle* h, int slot, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx) {
+  if (!h || slot < 0 || slot >= h->n_slots) return UBU_SW_ERR_ARG;
+  if (h->slots[slot].pending) return UBU_SW_ERR_BUSY;
+  CU(h, cudaSetDevice(h->device));
+  return do_stage(h, h->slots[slot], reads, windows, pair_ref_idx);
+}
+
+int ubu_sw_run(ubu_sw_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= h->n_slots) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  return do_run(h, h->slots[slot]);
+}
+
+int ubu_sw_sync(ubu_sw_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= h->n_slots) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->slots[slot].stream));
+  return UBU_SW_OK;
+}
+
+int ubu_sw_fetch(ubu_sw_handle* h, int slot, ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used) {
+  if (!h || slot < 0 || slot >= h->n_slots) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  return do_fetch(h, h->slots[slot], out, cigar_pool, cigar_pool_cap, cigar_pool_used);
+}
+
+int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]) {
+  if (!h || slot < 0 || slot >= h->n_slots || !ms) return UBU_SW_ERR_ARG;
+  Slot& s = h->slots[slot];
+  if (!s.ran) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaEventSynchronize(s.ev[2]));
+  CU(h, cudaEventElapsedTime(&ms[0], s.ev[0], s.ev[2]));
+  CU(h, cudaEventElapsedTime(&ms[1], s.ev[0], s.ev[1]));
+  CU(h, cudaEventElapsedTime(&ms[2], s.ev[1], s.ev[2]));
+  return UBU_SW_OK;
+}
+
+int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= h->n_slots) return UBU_SW_ERR_ARG;
+  return h->slots[slot].n_launches;
+}
+
+int ubu_sw_submit(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                  ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, int* ticket) {
+  if (!h || !ticket) return UBU_SW_ERR_ARG;
+  int slot = -1;
+  for (int k = 0; k < h->n_slots; ++k) {
+    const int c = (h->next_slot + k) % h->n_slots;
+    if (!h->slots[c].pending) { slot = c; break; }
+  }
+  if (slot < 0) return UBU_SW_ERR_BUSY;
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slots[slot];
+  int rc = do_stage(h, s, reads, windows, pair_ref_idx); if (rc) return rc;
+  rc = do_run(h, s); if (rc) return rc;
+  s.out = out; s.pool = cigar_pool; s.pool_cap = cigar_pool_cap; s.pending = true;
+  h->next_slot = (slot + 1) % h->n_slots;
+  *ticket = slot;
+  return UBU_SW_OK;
+}
+
+int ubu_sw_wait(ubu_sw_handle* h, int ticket, size_t* cigar_pool_used) {
+  if (!h || ticket < 0 || ticket >= h->n_slots) return UBU_SW_ERR_ARG;
+  Slot& s = h->slots[ticket];
+  if (!s.pending) return UBU_SW_ERR_BUSY;
+  CU(h, cudaSetDevice(h->device));
+  s.pending = false;
+  return do_fetch(h, s, s.out, s.pool, s.pool_cap, cigar_pool_used);
+}
+
+int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                       ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used) {
+  int ticket = -1;
+  int rc = ubu_sw_submit(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, &ticket);
+  if (rc) return rc;
+  return ubu_sw_wait(h, ticket, cigar_pool_used);
+}
+
+void* ubu_sw_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void ubu_sw_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// Sequence.java:10-13 (A=0 C=1 T=2 G=3), :31-41 (LSB first); case-folded, non-ACGT -> N plane (SPEC.md section 1).
+void ubu_sw_pack(const char* text, size_t n, uint8_t* packed, uint8_t* nmask, int* has_n) {
+  static int8_t code[256];
+  static bool init = false;
+  if (!init) {
+    for (int k = 0; k < 256; ++k) code[k] = -1;
+    code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['T'] = code['t'] = 2; code['G'] = code['g'] = 3;
+    init = true;
+  }
+  memset(packed, 0, (n + 3) / 4);
+  if (nmask) memset(nmask, 0, (n + 7) / 8);
+  int any = 0;
+  for (size_t k = 0; k < n; ++k) {
+    const int c = code[(unsigned char)text[k]];
+    if (c >= 0) packed[k >> 2] |= (uint8_t)(c << ((k & 3) * 2));
+    else { any = 1; if (nmask) nmask[k >> 3] |= (uint8_t)(1u << (k & 7)); }
+  }
+  if (has_n) *has_n = any;
+}
+
+// ReverseComplementor.java:15-22,38-62
+void ubu_sw_revcomp(const char* in, size_t n, char* out) {
+  for (size_t k = 0; k < n; ++k) {
+    char c = in[n - 1 - k];
+    switch (c) { case 'A': c = 'T'; break; case 'T': c = 'A'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; default: break; }
+    out[k] = c;
+  }
+}
+
+int ubu_sw_cigar_string(const uint32_t* ops, uint32_t n, char* buf, size_t cap) {
+  if (!buf || cap == 0) return 0;
+  if (n == 0) { if (cap >= 2) { buf[0] = '*'; buf[1] = 0; return 1; } buf[0] = 0; return 0; }
+  size_t w = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const char opc = "MIDNSHP=X"[(ops[k] & 15u) < 9 ? (ops[k] & 15u) : 0];
+    int m = snprintf(buf + w, cap - w, "%u%c", ops[k] >> 4, opc);
+    if (m < 0 || (size_t)m >= cap - w) { buf[w] = 0; return (int)w; }
+    w += (size_t)m;
+  }
+  return (int)w;
+}
+
+}  // extern "C"
