@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- SW realignment throughput (GCUPS, reads/s) on B200, one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the SPEC oracle on the box's host cores
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): 1M synthetic 76 bp paired-end
+reads (500k pairs, mates share a 500 bp window), affine gap, score + CIGAR. A "step" is one pass of
+the hot path (forward kernel + traceback kernels) over that batch = 3.8e10 full-matrix cells.
+For N > 1 every rank aligns its own shard of the same shape (weak scaling; reads shard trivially,
+no collective on the data path -- torch.distributed is used only for the barrier and the max-reduce
+of the timings).
+
+JSON keys follow the driver contract; see DESIGN.md section 6 for how each number is measured.
+There is no reference Java Smith-Waterman: the CPU arm is this repo's SPEC
+oracle ("port"), threads = all host cores, and is labelled as such.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN, WIN_LEN = 76, 500
+OPS_PER_CELL = 7.0 / 2.0          # 7 packed-lane ops per cell, two cells per 32-bit instruction
+
+
+def env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_int_peak() -> dict:
+    """P_int16x2 for the roofline: run bench/peak_int16x2 live if it is there, else the committed measurement."""
+    exe = os.path.join(ROOT, "bench", "peak_int16x2")
+    src = "live"
+    data = None
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=120).stdout
+            data = json.loads(out)
+        except Exception:
+            data = None
+    if data is None:
+        src = "profiles/peak_int16x2_r01.json (committed measurement)"
+        with open(os.path.join(ROOT, "profiles", "peak_int16x2_r01.json")) as f:
+            data = json.load(f)
+    return {"source": src, "roofline_gcups": data["roofline_gcups"], "instr_per_clk_per_sm": data["sw_mix_warp_instr_per_clk_per_sm"],
+            "sm_mhz": data["observed_sm_mhz"], "alu_only_roofline_gcups": data.get("alu_only_roofline_gcups")}
+
+
+def make_workload(n_reads: int, rank: int, keep_codes: bool):
+    from ubu_b200 import workloads as WL
+
+    seed = WL.SEEDS["cfg2"] + 7919 * rank
+    return WL.uniform("cfg2", n_reads, READ_LEN, WIN_LEN, seed=seed, paired=True, keep_codes=keep_codes)
+
+
+def cpu_arm(w, n_sample: int, threads: int, repeats: int = 1):
+    """Times the SPEC oracle (C, pthreads over tasks) on the first n_sample reads. Returns (gcups, reads/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+
+    import oracle_lib as O
+
+    n = min(n_sample, w.n_tasks)
+    q = np.ascontiguousarray(w.read_codes[:n]).reshape(-1)
+    nwin = int(w.pair_ref_idx[:n].max()) + 1 if w.pair_ref_idx is not None else n
+    r = np.ascontiguousarray(w.window_codes[:nwin]).reshape(-1)
+    qlen = np.full(n, READ_LEN, dtype=np.uint32); rlen = np.full(nwin, WIN_LEN, dtype=np.uint32)
+    qoff = (np.arange(n, dtype=np.uint64) * READ_LEN); roff = (np.arange(nwin, dtype=np.uint64) * WIN_LEN)
+    idx = None if w.pair_ref_idx is None else np.ascontiguousarray(w.pair_ref_idx[:n], dtype=np.uint32)
+    res = np.zeros(n, dtype=O.SWO_RESULT)
+    stride = READ_LEN + 8
+    cig = np.zeros(n * stride, dtype=np.uint32)
+    p = O.SwoParams(1, -3, 5, 2)
+    lib = O.lib()
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        st = lib.swo_align_batch(q.ctypes.data, qoff.ctypes.data, qlen.ctypes.data, r.ctypes.data, roff.ctypes.data, rlen.ctypes.data,
+                                 None if idx is None else idx.ctypes.data, n, C.byref(p), res.ctypes.data, cig.ctypes.data, stride, threads)
+        dt = time.perf_counter() - t0
+        assert st == 0
+        best = dt if best is None else min(best, dt)
+    cells = n * READ_LEN * WIN_LEN
+    return cells / best / 1e9, n / best, best, res
+
+
+def run_reference_arm(args):
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_sample = args.cpu_sample
+    w = make_workload(n_sample, 0, keep_codes=True)
+    for _ in range(max(args.warmup, 0)):
+        cpu_arm(w, min(n_sample, 20000), threads)
+    times = []
+    for _ in range(args.steps):
+        g, rps, dt, _ = cpu_arm(w, n_sample, threads)
+        times.append(dt)
+    dt = float(np.mean(times))
+    cells = n_sample * READ_LEN * WIN_LEN
+    gcups = cells / dt / 1e9
+    sample = f"{n_sample} of the 1,000,000 cfg2 reads per step (first {n_sample}, same generator and seed)"
+    line = {
+        "impl": "reference", "metric": "SW realignment GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "cfg2: 76 bp paired-end reads vs 500 bp windows, affine gap (+1/-3/5/2), score + CIGAR",
+                   "reads_per_step": n_sample, "note": "no Java Smith-Waterman exists in mozack/ubu (its Aligner forks bwa); "
+                   "this arm is this repo's SPEC oracle (oracle/sw_oracle.c), full-matrix 32-bit, pthreads over tasks"},
+        "reads_per_s": n_sample / dt,
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step (cfg2 = 1,000,000)")
+    ap.add_argument("--chunk", type=int, default=250_000, help="reads per submit() in the end-to-end leg")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the bounded CPU-oracle sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not (args.no_cpu and args.no_e2e):
+        args.warmup = 3            # timing hygiene: at least 3 warm-up steps
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+
+    import ubu_b200 as U
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.reads
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu)
+    w = make_workload(n, rank, keep_codes=want_cpu)
+    cells = float(w.cells)
+    al = U.SwAligner(device=local, slots=3)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    # ---------------- device-resident leg: inputs already in HBM ------------------------------------
+    al.stage(0, w.reads, w.windows, w.pair_ref_idx)
+    al.sync(0)
+    for _ in range(args.warmup):
+        al.run(0)
+    al.sync(0)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev_ms, fwd_ms, tb_ms = [], [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        torch.cuda.synchronize()
+        al.run(0)
+        al.sync(0)
+        m = al.last_run_ms(0)
+        ev_ms.append(m[0]); fwd_ms.append(m[1]); tb_ms.append(m[2])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = al.last_run_launches(0) * args.steps
+    dev_s = max_over_ranks(float(np.sum(ev_ms)) / 1e3)           # CUDA events on the launching stream, max over ranks
+    total_cells = sum_over_ranks(cells) * args.steps
+    total_reads = sum_over_ranks(float(n)) * args.steps
+    value = total_cells / dev_s / 1e9
+    fwd_s = float(np.mean(fwd_ms)) / 1e3
+    res0 = al.fetch(0, n)
+
+    # ---------------- end-to-end leg: host buffers in, host results out, every step -----------------
+    e2e = None
+    if not args.no_e2e:
+        chunk = min(args.chunk, n)
+        bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        # pinned host buffers for everything the library copies
+        def pin(a):
+            p = U.pinned_empty(a.shape, a.dtype); p[...] = a; return p
+        reads_p = U.SeqSet(pin(w.reads.packed), pin(w.reads.off), pin(w.reads.len), None, None)
+        wins_p = U.SeqSet(pin(w.windows.packed), pin(w.windows.off), pin(w.windows.len), None, None)
+        idx_p = pin(w.pair_ref_idx) if w.pair_ref_idx is not None else None
+        res_p = U.pinned_empty((n,), U.RESULT_DTYPE)
+        pool_cap = 6 * chunk + 4096
+        pools = [U.pinned_empty((pool_cap,), np.uint32) for _ in bounds]
+        h2d = d2h = 0
+
+        def one_pass(count_bytes: bool):
+            nonlocal h2d, d2h
+            inflight = []
+            for ci, (lo, hi) in enumerate(bounds):
+                if len(inflight) == al.slots:
+                    t, c = inflight.pop(0)
+                    used = al.wait(t)
+                    if count_bytes:
+                        d2h += used * 4
+                rs = reads_p.slice(lo, hi)
+                ix = None if idx_p is None else idx_p[lo:hi]
+                t = al.submit(rs, wins_p, ix, res_p[lo:hi], pools[ci])
+                inflight.append((t, ci))
+                if count_bytes:
+                    h2d += int(reads_p.packed.nbytes * (hi - lo) / n) + (hi - lo) * (4 + 2 + (4 if ix is not None else 0))
+                    h2d += int(wins_p.packed.nbytes) + wins_p.count * 6
+                    d2h += (hi - lo) * 32
+            for t, c in inflight:
+                used = al.wait(t)
+                if count_bytes:
+                    d2h += used * 4
+
+        for _ in range(max(args.warmup, 1)):
+            one_pass(False)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            one_pass(s == 0)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": total_cells / e2e_s / 1e9, "unit": "GCUPS", "reads_per_s": total_reads / e2e_s,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "how": f"ubu_sw_submit/ubu_sw_wait over {len(bounds)} chunks of {chunk} reads, {al.slots} slots in flight, pinned host "
+                      "buffers; the window set is re-sent with every chunk; timed by host clock between barriers"}
+        # the end-to-end results must equal the device-resident ones
+        same = all(np.array_equal(res_p[f], res0.results[f]) for f in ("score", "ref_start", "ref_end", "q_start", "q_end", "edit_distance", "cigar_n"))
+        e2e["matches_device_resident_results"] = bool(same)
+
+    # ---------------- roofline of the dominant kernel (forward pass) ----------------------------------
+    line = None
+    if rank == 0:
+        peak = measured_int_peak()
+        fwd_gcups = cells / fwd_s / 1e9
+        algo_bytes = (w.reads.packed.nbytes + w.windows.packed.nbytes + n * (4 + 2 + 4 + 4) + w.windows.count * 6 + n * 16)
+        roofline = {
+            "bound": "int_alu", "kernel": "sw_fwd16_kernel<G=8,K=10> (forward score pass)",
+            "achieved": fwd_gcups, "peak": peak["roofline_gcups"], "unit": "GCUPS", "frac": fwd_gcups / peak["roofline_gcups"],
+            "peak_source": f"bench/peak_int16x2.cu ({peak['source']}): {peak['instr_per_clk_per_sm']:.2f} warp-instr/clk/SM on the "
+                           f"4 ALU : 3 VIADD cell mix at {peak['sm_mhz']:.0f} MHz x 148 SMs x 32 lanes x 2 cells / 7 ops",
+            "alu_pipe_only_peak": peak.get("alu_only_roofline_gcups"),
+            "ops_per_cell": 7, "launch_ms": fwd_s * 1e3, "share_of_step": float(np.mean(fwd_ms) / np.mean(ev_ms)),
+            "traffic": None,
+            "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": 6551.4,
+                    "frac": algo_bytes / fwd_s / 1e9 / 6551.4, "note": "not the bound: ~2e-3 B/cell"},
+        }
+        line = {
+            "metric": "SW realignment GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
+            "config": {"workload": "cfg2: 1M synthetic 76 bp paired-end reads (500k pairs, mates share a window) vs 500 bp windows, "
+                                   "affine gap (+1/-3/5/2), score + CIGAR (BASELINE.json configs[1])",
+                       "reads_per_gpu_per_step": n, "cells_per_gpu_per_step": cells, "parallelism": f"shard{world}",
+                       "l2": "256 MB device buffer rewritten between timed steps (L2 flush), outside the CUDA-event pair"},
+            "reads_per_s": total_reads / dev_s,
+            "wall_s_timed_region": t_wall, "fwd_ms": float(np.mean(fwd_ms)), "traceback_ms": float(np.mean(tb_ms)),
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        unaligned = int((res0.results["flags"] & 1).sum())
+        line["sanity"] = {"unaligned": unaligned, "mean_score": float(res0.results["score"].mean())}
+
+    if want_cpu:
+        threads = os.cpu_count() or 1
+        ns = min(args.cpu_sample, n)
+        g, rps, dt, ores = cpu_arm(w, ns, threads)
+        agree = all(np.array_equal(ores[f], res0.results[f][:ns]) for f in ("score", "ref_start", "ref_end", "q_start", "q_end", "edit_distance"))
+        line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": "port", "reads_per_s": rps,
+                                "sample": f"first {ns} of the {n} reads of this run's workload, {dt:.2f} s wall; SPEC oracle "
+                                          "(oracle/sw_oracle.c, full-matrix 32-bit + traceback); NOT a reference Java aligner (none exists)",
+                                "gpu_results_match_on_sample": bool(agree)}
+    if rank == 0:
+        print(json.dumps(line))
+    al.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
