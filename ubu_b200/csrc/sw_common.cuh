@@ -16,7 +16,24 @@ struct DevSeqs {
   const uint32_t* nmask_off;
 };
 
-struct Scoring { int match, mismatch, gap_open, gap_ext; };
+struct Scoring {
+  int match, mismatch, gap_open, gap_ext;
+  // packed (v:v) 16-bit constants precomputed on the host: as kernel parameters they reach the packed
+  // instructions as constant-bank operands instead of costing a register-file read per use
+  uint32_t neg_oe2, neg_ext2, pos_oe2;
+};
+inline Scoring make_scoring(int match, int mismatch, int gap_open, int gap_ext) {
+  Scoring s; s.match = match; s.mismatch = mismatch; s.gap_open = gap_open; s.gap_ext = gap_ext;
+  const int oe = gap_open + gap_ext;
+  s.neg_oe2 = ((uint32_t)(-oe) & 0xFFFFu) * 0x00010001u;
+  s.neg_ext2 = ((uint32_t)(-gap_ext) & 0xFFFFu) * 0x00010001u;
+  s.pos_oe2 = ((uint32_t)oe & 0xFFFFu) * 0x00010001u;
+  return s;
+}
+
+// Per-column PRMT selector as kept in shared memory: 16 bits, or 32 when the window N flags ride along.
+template <bool HAS_N> struct SelType { using type = uint16_t; };
+template <> struct SelType<true> { using type = uint32_t; };
 
 // Output of the forward (score) pass, input of the traceback pass. 16 bytes.
 // The end column is exact; the end row is known to lie in [i_lo, i_hi] (the K rows one

@@ -35,10 +35,10 @@
 
 namespace ubu {
 
-template <bool HAS_N> struct SelType { using type = uint16_t; };
-template <> struct SelType<true> { using type = uint32_t; };
-
-template <int G, int K, bool HAS_N, int THREADS>
+// DEFAULT_SC = true compiles SPEC.md's default scoring (+1/-3/5/2) in as immediates: the packed
+// instructions then read two registers instead of three, which matters because the register file,
+// not just the ALU pipe, limits the dual-pipe issue rate (bench/rf_probe.cu).
+template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
                 const uint32_t* __restrict__ order, uint32_t n_slots, Scoring sc,
@@ -77,6 +77,7 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
   }
 
   // ---- per-row byte profiles (registers) ------------------------------------------------
+  if (DEFAULT_SC) { sc.match = 1; sc.mismatch = -3; sc.gap_open = 5; sc.gap_ext = 2; }
   const int oe = sc.gap_open + sc.gap_ext;
   const uint32_t mmb = (uint32_t)(sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(sc.match + oe) & 0xFFu;
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
@@ -92,18 +93,23 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
 
   // ---- per-column PRMT selectors (shared memory), index = column + G ----------------------
   SelT* sel = sel_all + (size_t)grp * sel_stride;
-  for (int idx = g; idx < sel_stride; idx += G) {
-    const int c = idx - G;
-    uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;             // padding column: sign-replicate selectors
-    if (c >= 0 && c < WA) {
-      const uint32_t b = base2(rA, c); lo = b | ((b | 8u) << 4);
-      if (HAS_N && rnA && nbit(rnA, c)) nf |= 0x00800000u;
+  // one byte of each window = 4 columns = 4 selectors per trip (sel_stride and G are multiples of 4)
+  for (int q4 = g; q4 < sel_stride / 4; q4 += G) {
+    const int c0 = 4 * q4 - G;                              // first column of this quad (byte c0 / 4 of the window)
+    uint32_t byA = 0u, byB = 0u, nA = 0u, nB = 0u;
+    if (c0 >= 0 && c0 < WA) { byA = rA[c0 >> 2]; if (HAS_N && rnA) nA = (uint32_t)(rnA[c0 >> 3] >> (c0 & 4)) & 15u; }
+    if (c0 >= 0 && c0 < WB) { byB = rB[c0 >> 2]; if (HAS_N && rnB) nB = (uint32_t)(rnB[c0 >> 3] >> (c0 & 4)) & 15u; }
+    SelT out4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;             // padding column: sign-replicate selectors
+      if (c >= 0 && c < WA) { const uint32_t b = (byA >> (2 * j)) & 3u; lo = b | ((b | 8u) << 4); if (HAS_N && ((nA >> j) & 1u)) nf |= 0x00800000u; }
+      if (c >= 0 && c < WB) { const uint32_t b = ((byB >> (2 * j)) & 3u) + 4u; hi = b | ((b | 8u) << 4); if (HAS_N && ((nB >> j) & 1u)) nf |= 0x80000000u; }
+      out4[j] = (SelT)(lo | (hi << 8) | nf);
     }
-    if (c >= 0 && c < WB) {
-      const uint32_t b = base2(rB, c) + 4u; hi = b | ((b | 8u) << 4);
-      if (HAS_N && rnB && nbit(rnB, c)) nf |= 0x80000000u;
-    }
-    sel[idx] = (SelT)(lo | (hi << 8) | nf);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sel[4 * q4 + j] = out4[j];
   }
   __syncthreads();
   if (g == 0) atomicMax(&s_wmax, max(WA, WB));
@@ -111,7 +117,8 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
   const int nsteps = s_wmax > 0 ? s_wmax + G - 1 : 0;
 
   // ---- systolic sweep ---------------------------------------------------------------------
-  const uint32_t NEG_OE = pack16x2(-oe), NEG_EXT = pack16x2(-sc.gap_ext), POS_OE = pack16x2(oe);
+  const uint32_t NEG_OE = DEFAULT_SC ? 0xFFF9FFF9u : sc.neg_oe2, NEG_EXT = DEFAULT_SC ? 0xFFFEFFFEu : sc.neg_ext2,
+                 POS_OE = DEFAULT_SC ? 0x00070007u : sc.pos_oe2;
   uint32_t Hoe[K], E[K];
 #pragma unroll
   for (int r = 0; r < K; ++r) { Hoe[r] = NEG_OE; E[r] = NEG_OE; }
@@ -119,30 +126,39 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
   uint32_t best = 0u; int stepA = 0, stepB = 0;
   const SelT* selp = sel + (G - g);                       // selp[s] = selector of column s - g
 
+  // boundary fix-up of lane 0 done with one IMAD per shuffle (FMA pipe) instead of a select (ALU pipe)
+  uint32_t bmul = (g == 0) ? 0u : 1u;
+  const uint32_t badd = (g == 0) ? NEG_OE : 0u;
+  asm volatile("" : "+r"(bmul));                          // opaque, so the multiply is not folded back into a select
+
 #pragma unroll 1
   for (int s = 0; s < nsteps; ++s) {
     const uint32_t selv = selp[s];
-    uint32_t up = __shfl_up_sync(0xffffffffu, hoe_bot, 1, G);
-    uint32_t F = __shfl_up_sync(0xffffffffu, f_bot, 1, G);
-    if (g == 0) { up = NEG_OE; F = NEG_OE; }              // row 0: H[0][j] = 0, F[1][j] = -oe
+    const uint32_t up = __shfl_up_sync(0xffffffffu, hoe_bot, 1, G) * bmul + badd;   // row 0: H[0][j] = 0
+    uint32_t F = __shfl_up_sync(0xffffffffu, f_bot, 1, G) * bmul + badd;            // row 0: F[1][j] = -oe
     uint32_t hd = hoe_up_prev;                            // H[top-1][j-1] - oe
     hoe_up_prev = up;
     uint32_t isn = 0u;
-    if (HAS_N) isn = prmt(selv, 0u, 0xBBAAu);      // 0xFFFF per half whose window base is N
-    uint32_t colmax = 0u, hprev = 0u;
+    if (HAS_N) isn = prmt(selv, 0u, 0xBBAAu);             // 0xFFFF per half whose window base is N
+    // The running max is taken over t = Hdiag + s instead of H: the arg-max cell of a local alignment is
+    // always entered diagonally (SPEC.md section 5), so max t == max H with identical positions, and
+    // giving t a second consumer keeps the add on the second integer pipe (ptxas would otherwise fuse
+    // add+max into a second ALU-pipe VIADDMNMX).
+    uint32_t colmax = 0u, tprev = 0u;
 #pragma unroll
     for (int r = 0; r < K; ++r) {
-      uint32_t sp = prmt(profA[r], profB[r], selv & 0xFFFFu);       // (s+oe) of B : A
+      uint32_t sp = prmt(profA[r], profB[r], selv & 0xFFFFu);               // (s+oe) of B : A      [ALU]
       if (HAS_N) sp = (sp & ~isn) | (POS_OE & isn);                          // window N scores 0
-      E[r] = __viaddmax_s16x2(E[r], NEG_EXT, Hoe[r]);                        // E[i][j]
-      const uint32_t t = __vadd2(hd, sp);                                    // H[i-1][j-1] + s
+      const uint32_t t = __vadd2(hd, sp);                                    // H[i-1][j-1] + s      [pipe 2]
       hd = Hoe[r];
-      const uint32_t h = __vimax3_s16x2_relu(t, E[r], F);                    // H[i][j]
-      Hoe[r] = __vadd2(h, NEG_OE);
-      F = __viaddmax_s16x2(F, NEG_EXT, Hoe[r]);                              // F[i+1][j]
-      if (r & 1) colmax = __vimax3_s16x2(colmax, hprev, h); else hprev = h;
+      E[r] = __viaddmax_s16x2(E[r], NEG_EXT, Hoe[r]);                        // E[i][j]              [ALU]
+      const uint32_t fx = __vadd2(F, NEG_EXT);                               // F[i][j] - ext        [pipe 2]
+      const uint32_t h = __vimax3_s16x2_relu(t, E[r], F);                    // H[i][j]              [ALU]
+      Hoe[r] = __vadd2(h, NEG_OE);                                           //                      [pipe 2]
+      F = __viaddmax_s16x2(h, NEG_OE, fx);                                   // F[i+1][j]            [ALU]
+      if (r & 1) colmax = __vimax3_s16x2(colmax, tprev, t); else tprev = t;  //                      [ALU, 1 per 2 rows]
     }
-    if (K & 1) colmax = __vmaxs2(colmax, hprev);
+    if (K & 1) colmax = __vmaxs2(colmax, tprev);
     hoe_bot = Hoe[K - 1]; f_bot = F;
     bool keep_hi, keep_lo;                                                   // true = old best >= column max
     best = vmax2_keep(best, colmax, keep_hi, keep_lo);

@@ -3,23 +3,37 @@
 // Input per task is the forward pass's (S, je, [i_lo,i_hi]). By the gap bound of SPEC.md section 7
 // the SPEC traceback path from any candidate end cell (i, je), i in [i_lo,i_hi], stays inside the
 // diagonal band  d = j - i  in  [je - i_hi - Gb, je - i_lo + Gb],  Gb = gap_bound(i_hi, S).
-// The band is re-filled with exact 32-bit SPEC arithmetic (cells outside the band / matrix act as
-// H = 0, E = F = -inf), 4 direction bits per cell are kept, and the SPEC state machine is replayed
-// on those bits. Banded values are <= the full-matrix values everywhere and equal on the SPEC path
-// (DESIGN.md section 4), so every decision -- including tie-breaks -- is the full-matrix decision.
 //
-// Kernels: tb_plan_kernel sorts tasks into band-width classes; tb_band_kernel<BW> keeps the band
-// rows in registers (one thread per task, BW = 16 or 32 diagonals); tb_wide_kernel handles any
-// wider band with the band rows in a per-thread global scratch (rare: low-scoring tasks).
-// Direction bits live in a per-thread global scratch, interleaved so that a warp's row write is
-// one contiguous 256-byte store.
+// FILL. The band is re-filled with the same packed 16-bit arithmetic as the forward pass, two tasks
+// per thread (task A in the low, task B in the high half), one band row per loop trip; only H is
+// stored (one packed word per band cell). Cells left of column 1 see padding selectors (score <= 0
+// after bias), so they evaluate to H = 0, E = F = -oe, which is what the matrix boundary needs;
+// cells right of column je only feed cells right of column je. Banded values are <= the full-matrix
+// values everywhere and equal on the SPEC path.
+//
+// WALK. The SPEC state machine is replayed from stored H values alone:
+//   * stop when the running score reaches 0 (H along the path is the running score);
+//   * diagonal first:  H[i-1][j-1] + s(q_i, r_j) == H[i][j];
+//   * else read-gap (I) if some k has H[i-k][j] - open - k*ext == H[i][j]; SPEC's "extension preferred
+//     over gap-close" picks the LARGEST such k (an extension step at row x exists iff some k' >= 2
+//     reproduces the value from row x, so the chain runs to the farthest opener);
+//   * else window-gap (D), same rule along the row.
+// A comparison that holds in the full matrix involves a cell of the SPEC path (exact in the band);
+// one that fails in the full matrix fails a fortiori with banded values (they are lower bounds).
+//
+// Kernels: tb_plan_kernel sorts tasks into band-width classes; tb_fill_reg_kernel<BW> keeps the
+// band row in registers (BW = 16 or 32 diagonals); tb_fill_smem_kernel keeps it in shared memory
+// (any width that fits); tb_wide_kernel (scalar, global scratch, direction bits) is the last resort
+// for bands too wide for shared memory (extreme scoring parameters only).
 #pragma once
 #include "sw_common.cuh"
 
 namespace ubu {
 
 constexpr int TB_NEG = -0x10000000;
-constexpr int TB_CLASSES = 3;     // 0: band <= 16 (registers), 1: band <= 32 (registers), 2: wide (global scratch)
+// band-width classes: 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 (registers),
+// 4: shared-memory band, 5: scalar last resort
+constexpr int TB_CLASSES = 6;
 
 struct TbArgs {
   DevSeqs reads, wins;
@@ -33,9 +47,25 @@ struct TbArgs {
   unsigned int* err_flag;        // bit 0: pool overflow, bit 1: internal inconsistency
 };
 
+// Band geometry of one task (SPEC.md section 7).
+struct Band {
+  int S, je, i_lo, i_hi, d_lo, bw, i_first, rows, c0;
+};
+__host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdOut& f, int bw_fixed) {
+  Band g;
+  g.S = f.score; g.je = f.je; g.i_lo = f.i_lo; g.i_hi = f.i_hi;
+  const int Gb = gap_bound(sc, f.i_hi, f.score);
+  g.d_lo = f.je - f.i_hi - Gb;
+  g.bw = bw_fixed > 0 ? bw_fixed : (f.i_hi - f.i_lo) + 2 * Gb + 1;
+  g.i_first = 2 - g.d_lo - g.bw; if (g.i_first < 1) g.i_first = 1;     // first row whose band touches column 1
+  g.rows = f.i_hi - g.i_first + 1;
+  g.c0 = g.i_first + g.d_lo - 1;                                       // 0-based window column of cell (row 0, b = 0)
+  return g;
+}
+
 // ---- classify ------------------------------------------------------------------------------
 __global__ void tb_plan_kernel(const uint32_t* __restrict__ order, uint32_t n_slots, const FwdOut* __restrict__ fwd,
-                               Scoring sc, ubu_sw_result* __restrict__ res,
+                               Scoring sc, int smem_bw_cap, ubu_sw_result* __restrict__ res,
                                uint32_t* __restrict__ lists /* [TB_CLASSES][n_slots] */, unsigned int* __restrict__ counts) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1; uint32_t task = 0xFFFFFFFFu;
@@ -47,8 +77,9 @@ __global__ void tb_plan_kernel(const uint32_t* __restrict__ order, uint32_t n_sl
       r.cigar_off = 0; r.cigar_n = 0; r.flags = UBU_SW_FLAG_UNALIGNED;
       res[task] = r;
     } else {
-      const int bw = (f.i_hi - f.i_lo) + 2 * gap_bound(sc, f.i_hi, f.score) + 1;
-      cls = bw <= 16 ? 0 : (bw <= 32 ? 1 : 2);
+      const int gb = gap_bound(sc, f.i_hi, f.score);
+      const int bw = (f.i_hi - f.i_lo) + 2 * gb + 1;
+      cls = gb == 0 ? 0 : (bw <= 8 ? 1 : (bw <= 16 ? 2 : (bw <= 32 ? 3 : (bw <= smem_bw_cap ? 4 : 5))));
     }
   }
   const unsigned lane = threadIdx.x & 31u;
@@ -79,12 +110,12 @@ __device__ __forceinline__ TaskView load_task(const TbArgs& a, uint32_t task) {
   return t;
 }
 
-// Appends (len, op) runs in walk order (back to front); emit() reverses into the pool.
+// Appends (len, op) runs in walk order (back to front); emit_result() reverses into the pool.
 struct OpRuns {
   uint32_t* ops; int n; int cur_op; uint32_t cur_len;
   __device__ __forceinline__ void init(uint32_t* buf) { ops = buf; n = 0; cur_op = -1; cur_len = 0; }
   __device__ __forceinline__ void flush() { if (cur_len) ops[n++] = (cur_len << 4) | (uint32_t)cur_op; cur_len = 0; }
-  __device__ __forceinline__ void push(int op) { if (op != cur_op) { flush(); cur_op = op; } ++cur_len; }
+  __device__ __forceinline__ void push(int op, uint32_t len) { if (op != cur_op) { flush(); cur_op = op; } cur_len += len; }
   __device__ __forceinline__ void push_run(int op, uint32_t len) { if (len) { flush(); cur_op = -1; ops[n++] = (len << 4) | (uint32_t)op; } }
 };
 
@@ -103,129 +134,264 @@ __device__ __forceinline__ void emit_result(const TbArgs& a, uint32_t task, cons
   a.res[task] = r;
 }
 
-// Replays the SPEC section 5 state machine on the stored direction nibbles.
-//   nibble: bits 0-1 = H source (0 stop, 1 diagonal, 2 F, 3 E), bit 2 = F came by extension, bit 3 = E came by extension
-// DirAt(row_index, b) returns the nibble of band cell b in row i (row_index = i - i_first).
-template <class DirAt>
-__device__ __forceinline__ void walk_and_emit(const TbArgs& a, uint32_t task, const TaskView& t, int S, int ie, int je,
-                                              int d_lo, int i_first, int bw, uint32_t* opbuf, DirAt dir_at) {
+// Walk on stored H values (see the header comment). HAt(n, b) returns H of band cell b in band row n
+// (n = i - i_first) for THIS task's half; rows above i_first / columns left of 1 are the zero boundary.
+template <class HAt>
+__device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, const TaskView& t, const Band& g, int bw,
+                                                uint32_t* opbuf, HAt h_at) {
+  const int ma = a.sc.match, mm = a.sc.mismatch, open = a.sc.gap_open, ext = a.sc.gap_ext;
+  // SPEC section 4: smallest row among the candidates that reaches S in column je
+  int ie = 0;
+  for (int i = g.i_lo; i <= g.i_hi; ++i) {
+    if (h_at(i - g.i_first, g.je - i - g.d_lo) == g.S) { ie = i; break; }
+  }
+  if (ie == 0) { atomicOr(a.err_flag, 2u); return; }
   OpRuns o; o.init(opbuf);
   o.push_run(UBU_SW_CIGAR_S, (uint32_t)(t.L - ie));
-  int i = ie, j = je, state = 0, edits = 0;
+  int i = ie, j = g.je, h = g.S, edits = 0;
   bool bad = false;
-  while (true) {
-    if (i < 1 || j < 1) { if (state != 0) bad = true; break; }
-    const int b = j - i - d_lo;
-    if (b < 0 || b >= bw || i < i_first) { bad = true; break; }
-    const uint32_t nib = dir_at(i - i_first, b);
-    if (state == 0) {
-      const uint32_t src = nib & 3u;
-      if (src == 0u) break;
-      if (src == 1u) {
-        o.push(UBU_SW_CIGAR_M);
-        const uint32_t qc = base2(t.q, (uint32_t)(i - 1)), rc = base2(t.r, (uint32_t)(j - 1));
-        const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1))) || (t.rn && nbit(t.rn, (uint32_t)(j - 1)));
-        if (qc != rc && !isn) ++edits;
-        --i; --j;
-      } else state = (src == 2u) ? 1 : 2;
-    } else if (state == 1) {
-      o.push(UBU_SW_CIGAR_I); ++edits;
-      --i; if (!(nib & 4u)) state = 0;
-    } else {
-      o.push(UBU_SW_CIGAR_D); ++edits;
-      --j; if (!(nib & 8u)) state = 0;
+  while (h > 0) {
+    const int n = i - g.i_first, b = j - i - g.d_lo;
+    if (i < 1 || j < 1 || n < 0 || b < 0 || b >= bw) { bad = true; break; }
+    // diagonal
+    const uint32_t qc = base2(t.q, (uint32_t)(i - 1)), rc = base2(t.r, (uint32_t)(j - 1));
+    const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1))) || (t.rn && nbit(t.rn, (uint32_t)(j - 1)));
+    const int s = isn ? 0 : (qc == rc ? ma : mm);
+    const int hdg = (n >= 1 && j >= 2) ? h_at(n - 1, b) : 0;
+    if (hdg + s == h) {
+      o.push(UBU_SW_CIGAR_M, 1u);
+      if (!isn && qc != rc) ++edits;
+      --i; --j; h = hdg;
+      continue;
     }
+    // read gap (I): largest k with H[i-k][j] - open - k*ext == h
+    int kbest = 0;
+    for (int k = 1; k <= n && b + k < bw; ++k) {
+      const int need = h + open + k * ext;              // required H[i-k][j]
+      if (need > g.S) break;
+      if (h_at(n - k, b + k) == need) kbest = k;
+    }
+    if (kbest) {
+      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); edits += kbest;
+      i -= kbest; h += open + kbest * ext;
+      continue;
+    }
+    // window gap (D): largest k with H[i][j-k] - open - k*ext == h
+    for (int k = 1; k <= b && j - k >= 1; ++k) {
+      const int need = h + open + k * ext;
+      if (need > g.S) break;
+      if (h_at(n, b - k) == need) kbest = k;
+    }
+    if (kbest) {
+      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); edits += kbest;
+      j -= kbest; h += open + kbest * ext;
+      continue;
+    }
+    bad = true; break;
   }
   o.flush();
   o.push_run(UBU_SW_CIGAR_S, (uint32_t)i);     // q_start - 1 = i
-  if (bad) atomicOr(a.err_flag, 2u);
-  emit_result(a, task, o, S, j + 1, je, i + 1, ie, edits);
+  if (bad) { atomicOr(a.err_flag, 2u); return; }
+  emit_result(a, task, o, g.S, j + 1, g.je, i + 1, ie, edits);
 }
 
-// ---- register band kernel ------------------------------------------------------------------
-// dir scratch: word (row*NW + w) of thread gtid at dir[((row*NW + w) * nthreads) + gtid]
-template <int BW, bool HAS_N, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-tb_band_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
-               unsigned long long* __restrict__ dir, int max_rows) {
-  constexpr int NW = BW / 16;
+// ---- class 0: no gap fits under the score (Gb == 0) ---------------------------------------------
+// Every path of score S ending in a candidate cell is gap-free, so H[i][je] == S iff the best purely
+// diagonal local score ending there is S, and the SPEC walk is the diagonal itself: accumulate scores
+// backwards from (i, je); the first time the sum reaches S the running H hits 0 (SPEC stop).
+__global__ void __launch_bounds__(128)
+tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count) {
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = *count;
-  const int ma = a.sc.match, mm = a.sc.mismatch, ext = a.sc.gap_ext, oe = a.sc.gap_open + a.sc.gap_ext;
-  uint32_t opbuf[BW + 8];
-
+  const int ma = a.sc.match, mm = a.sc.mismatch;
   for (uint32_t idx = gtid; idx < n; idx += nthreads) {
     const uint32_t task = list[idx];
     const FwdOut f = a.fwd[task];
     const TaskView t = load_task(a, task);
-    const int S = f.score, je = f.je, i_lo = f.i_lo, i_hi = f.i_hi;
-    const int Gb = gap_bound(a.sc, i_hi, S);
-    const int d_lo = je - i_hi - Gb;
-    const int i_first = max(1, 2 - d_lo - BW);                 // first row whose band touches column 1
-    if (i_hi - i_first + 1 > max_rows) { atomicOr(a.err_flag, 2u); continue; }
-
-    // sliding window of the window's bases for the band cells of the current row (16 bases / word)
-    uint32_t rwin[NW]; uint32_t nwin = 0u;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) rwin[w] = 0u;
-#pragma unroll
-    for (int b = 0; b < BW; ++b) {
-      const int c = i_first + d_lo + b - 1;
-      if (c >= 0 && c < t.W) {
-        rwin[b / 16] |= base2(t.r, (uint32_t)c) << (2 * (b % 16));
-        if (HAS_N && t.rn) nwin |= nbit(t.rn, (uint32_t)c) << b;
+    const int S = f.score, je = f.je;
+    int ie = 0, len = 0, edits = 0;
+    for (int i = f.i_lo; i <= f.i_hi && !ie; ++i) {
+      const int maxk = min(i, je);
+      int run = 0, mism = 0;
+      for (int k = 0; k < maxk; ++k) {
+        const uint32_t qc = base2(t.q, (uint32_t)(i - 1 - k)), rc = base2(t.r, (uint32_t)(je - 1 - k));
+        const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1 - k))) || (t.rn && nbit(t.rn, (uint32_t)(je - 1 - k)));
+        const bool eq = qc == rc;
+        run += isn ? 0 : (eq ? ma : mm);
+        mism += (!isn && !eq) ? 1 : 0;
+        if (run == S) { ie = i; len = k + 1; edits = mism; break; }
+        if (run + (maxk - 1 - k) * ma < S) break;            // S is out of reach on this diagonal
       }
     }
-    int H[BW], F[BW];
-#pragma unroll
-    for (int b = 0; b < BW; ++b) { H[b] = 0; F[b] = TB_NEG; }
-    int ie = 0;
-
-    for (int i = i_first; i <= i_hi; ++i) {
-      const uint32_t qc = base2(t.q, (uint32_t)(i - 1));
-      const bool qn = HAS_N && t.qn && nbit(t.qn, (uint32_t)(i - 1));
-      const int bmin = max(0, 1 - i - d_lo), bmax = min(BW - 1, je - i - d_lo);
-      int hleft = 0, eleft = TB_NEG, hend = -1;
-      unsigned long long word = 0ull;
-      const size_t rowbase = (size_t)(i - i_first) * NW;
-#pragma unroll
-      for (int b = 0; b < BW; ++b) {
-        const int upH = (b + 1 < BW) ? H[b + 1] : 0, upF = (b + 1 < BW) ? F[b + 1] : TB_NEG;
-        const int fe = upF - ext, fo = upH - oe;
-        int fv = max(fe, fo);
-        const int ee = eleft - ext, eo = hleft - oe;
-        int ev = max(ee, eo);
-        const bool ismatch = (((rwin[b / 16] >> (2 * (b % 16))) & 3u) == qc);
-        int s = ismatch ? ma : mm;
-        if (HAS_N) { if (qn || ((nwin >> b) & 1u)) s = 0; }
-        const int d = H[b] + s;
-        int h = max(max(d, ev), max(fv, 0));
-        uint32_t nib = (h == 0) ? 0u : (h == d) ? 1u : (h == fv) ? 2u : 3u;
-        nib |= (fe >= fo ? 4u : 0u) | (ee >= eo ? 8u : 0u);
-        if (b < bmin || b > bmax) { h = 0; ev = TB_NEG; fv = TB_NEG; nib = 0u; }
-        if (b == bmax) hend = h;
-        word |= (unsigned long long)nib << (4 * (b % 16));
-        H[b] = h; F[b] = fv; hleft = h; eleft = ev;
-        if ((b % 16) == 15) { dir[(rowbase + b / 16) * nthreads + gtid] = word; word = 0ull; }
-      }
-      if (ie == 0 && i >= i_lo && hend == S) ie = i;           // smallest i with H[i][je] == S
-      // slide the base window one column to the right
-      const int cn = i + d_lo + BW - 1;                        // 0-based column entering at b = BW-1 for row i+1
-      uint32_t nb = 0u, nn = 0u;
-      if (cn >= 0 && cn < t.W) { nb = base2(t.r, (uint32_t)cn); if (HAS_N && t.rn) nn = nbit(t.rn, (uint32_t)cn); }
-#pragma unroll
-      for (int w = 0; w < NW; ++w) rwin[w] = (rwin[w] >> 2) | ((w + 1 < NW ? rwin[w + 1] : nb) << 30);
-      if (HAS_N) nwin = (nwin >> 1) | (nn << (BW - 1));
-    }
-    if (ie == 0) { atomicOr(a.err_flag, 2u); continue; }
-    walk_and_emit(a, task, t, S, ie, je, d_lo, i_first, BW, opbuf,
-                  [&](int row, int b) -> uint32_t {
-                    return (uint32_t)(dir[((size_t)row * NW + b / 16) * nthreads + gtid] >> (4 * (b % 16))) & 15u;
-                  });
+    if (!ie) { atomicOr(a.err_flag, 2u); continue; }
+    uint32_t ops[3]; int no = 0;                              // front to back
+    if (ie - len > 0) ops[no++] = ((uint32_t)(ie - len) << 4) | UBU_SW_CIGAR_S;
+    ops[no++] = ((uint32_t)len << 4) | UBU_SW_CIGAR_M;
+    if (t.L - ie > 0) ops[no++] = ((uint32_t)(t.L - ie) << 4) | UBU_SW_CIGAR_S;
+    ubu_sw_result r;
+    r.score = S; r.ref_start = je - len + 1; r.ref_end = je; r.q_start = ie - len + 1; r.q_end = ie; r.edit_distance = edits;
+    r.flags = 0; r.cigar_n = (uint16_t)no;
+    const unsigned off = atomicAdd(a.cig_cursor, (unsigned)no);
+    r.cigar_off = off;
+    if (off + (unsigned)no <= a.cig_cap) { for (int k = 0; k < no; ++k) a.cig_pool[off + k] = ops[k]; }
+    else atomicOr(a.err_flag, 1u);
+    a.res[task] = r;
   }
 }
 
-// ---- wide band kernel (band rows in global scratch; any width) --------------------------------
+// Per-row byte profile of one read base (same encoding as the forward pass).
+__device__ __forceinline__ uint32_t row_profile(const TaskView& t, int i /*1-based*/, uint32_t MM4, uint32_t MX, uint32_t N4) {
+  if (i < 1 || i > t.L) return 0x80808080u;
+  if (t.qn && nbit(t.qn, (uint32_t)(i - 1))) return N4;
+  return MM4 ^ (MX << (8u * base2(t.q, (uint32_t)(i - 1))));
+}
+
+// Selector of band column k (0-based window columns cA, cB) for the pair; padding outside [0, W).
+template <bool HAS_N>
+__device__ __forceinline__ uint32_t pair_selector(const TaskView& ta, const TaskView& tb, int cA, int cB) {
+  uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;
+  if (cA >= 0 && cA < ta.W) {
+    const uint32_t b = base2(ta.r, (uint32_t)cA); lo = b | ((b | 8u) << 4);
+    if (HAS_N && ta.rn && nbit(ta.rn, (uint32_t)cA)) nf |= 0x00800000u;
+  }
+  if (cB >= 0 && cB < tb.W) {
+    const uint32_t b = base2(tb.r, (uint32_t)cB) + 4u; hi = b | ((b | 8u) << 4);
+    if (HAS_N && tb.rn && nbit(tb.rn, (uint32_t)cB)) nf |= 0x80000000u;
+  }
+  return lo | (hi << 8) | nf;
+}
+
+// ---- register band fill + walk: one thread = one PAIR of tasks ---------------------------------
+// hstore: packed H of band cell (n, b) of thread gtid at hstore[(n*BW + b) * nthreads + gtid]
+// selectors: shared memory, sel[k * THREADS + tid], k = n + b
+template <int BW, bool HAS_N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
+                   uint32_t* __restrict__ hstore, int max_rows) {
+  using SelT = typename SelType<HAS_N>::type;
+  extern __shared__ __align__(16) unsigned char tb_smem[];
+  SelT* sel = reinterpret_cast<SelT*>(tb_smem);
+  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t n_tasks = *count, n_pairs = (n_tasks + 1u) / 2u;
+  const int oe = a.sc.gap_open + a.sc.gap_ext;
+  const uint32_t mmb = (uint32_t)(a.sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(a.sc.match + oe) & 0xFFu;
+  const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
+  const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
+  uint32_t opbuf[BW + 8];
+
+  for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
+    const uint32_t tA = list[2u * pair];
+    const bool haveB = 2u * pair + 1u < n_tasks;
+    const uint32_t tB = haveB ? list[2u * pair + 1u] : tA;
+    const TaskView va = load_task(a, tA), vb = load_task(a, tB);
+    const Band ga = make_band(a.sc, a.fwd[tA], BW), gb = make_band(a.sc, a.fwd[tB], BW);
+    const int nrows = max(ga.rows, gb.rows);
+    if (nrows > max_rows) { atomicOr(a.err_flag, 2u); continue; }
+
+    for (int k = 0; k < nrows + BW - 1; ++k) sel[k * THREADS + tid] = (SelT)pair_selector<HAS_N>(va, vb, ga.c0 + k, gb.c0 + k);
+
+    uint32_t Hd[BW], Fv[BW];
+#pragma unroll
+    for (int b = 0; b < BW; ++b) { Hd[b] = NEG_OE; Fv[b] = NEG_OE; }
+    for (int n = 0; n < nrows; ++n) {
+      const uint32_t pa = row_profile(va, ga.i_first + n, MM4, MX, N4);
+      const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
+      uint32_t e = NEG_OE, hoe_left = NEG_OE;
+      const SelT* srow = sel + (size_t)n * THREADS + tid;
+      uint32_t* hrow = hstore + ((size_t)n * BW) * nthreads + gtid;
+#pragma unroll
+      for (int b = 0; b < BW; ++b) {
+        const uint32_t selv = srow[b * THREADS];
+        uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
+        if (HAS_N) { const uint32_t isn = prmt(selv, 0u, 0xBBAAu); sp = (sp & ~isn) | (POS_OE & isn); }
+        const uint32_t t = __vadd2(Hd[b], sp);                                  // H[i-1][j-1] + s
+        const uint32_t up_hoe = (b + 1 < BW) ? Hd[b + 1] : NEG_OE, up_f = (b + 1 < BW) ? Fv[b + 1] : NEG_OE;
+        const uint32_t f = __viaddmax_s16x2(up_f, NEG_EXT, up_hoe);             // F[i][j]
+        e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);                              // E[i][j]
+        const uint32_t h = __vimax3_s16x2_relu(t, e, f);
+        const uint32_t hoe = __vadd2(h, NEG_OE);
+        hrow[(size_t)b * nthreads] = h;
+        Hd[b] = hoe; Fv[b] = f; hoe_left = hoe;
+      }
+    }
+    walk_h_and_emit(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> int {
+      return (int)(hstore[((size_t)n * BW + b) * nthreads + gtid] & 0xFFFFu);
+    });
+    if (haveB)
+      walk_h_and_emit(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> int {
+        return (int)(hstore[((size_t)n * BW + b) * nthreads + gtid] >> 16);
+      });
+  }
+}
+
+// ---- shared-memory band fill + walk (any band width up to bw_cap) ---------------------------------
+// shared memory per CTA: Hd[bw_cap][THREADS] u32, Fv[bw_cap][THREADS] u32, sel[(max_rows + bw_cap)][THREADS] SelT
+// hstore: cell (n, b) of thread gtid at hstore[(n * bw + b) * nthreads + gtid]   (bw = this pair's width; n*bw+b < max_rows*bw_cap)
+template <bool HAS_N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
+                    uint32_t* __restrict__ hstore, uint32_t* __restrict__ opscratch, int max_rows, int bw_cap) {
+  using SelT = typename SelType<HAS_N>::type;
+  extern __shared__ __align__(16) unsigned char tb_smem[];
+  uint32_t* Hd = reinterpret_cast<uint32_t*>(tb_smem);
+  uint32_t* Fv = Hd + (size_t)bw_cap * THREADS;
+  SelT* sel = reinterpret_cast<SelT*>(Fv + (size_t)bw_cap * THREADS);
+  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t n_tasks = *count, n_pairs = (n_tasks + 1u) / 2u;
+  const int oe = a.sc.gap_open + a.sc.gap_ext;
+  const uint32_t mmb = (uint32_t)(a.sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(a.sc.match + oe) & 0xFFu;
+  const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
+  const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
+  uint32_t* hmine = hstore + gtid;
+  uint32_t* opbuf = opscratch + (size_t)gtid * (size_t)(2 * bw_cap + max_rows + 8);
+
+  for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
+    const uint32_t tA = list[2u * pair];
+    const bool haveB = 2u * pair + 1u < n_tasks;
+    const uint32_t tB = haveB ? list[2u * pair + 1u] : tA;
+    const TaskView va = load_task(a, tA), vb = load_task(a, tB);
+    const Band na = make_band(a.sc, a.fwd[tA], 0), nb = make_band(a.sc, a.fwd[tB], 0);
+    const int bw = max(na.bw, nb.bw);                         // both halves sweep the wider band
+    const Band ga = make_band(a.sc, a.fwd[tA], bw), gb = make_band(a.sc, a.fwd[tB], bw);
+    const int nrows = max(ga.rows, gb.rows);
+    if (nrows > max_rows || bw > bw_cap) { atomicOr(a.err_flag, 2u); continue; }
+
+    for (int k = 0; k < nrows + bw - 1; ++k) sel[k * THREADS + tid] = (SelT)pair_selector<HAS_N>(va, vb, ga.c0 + k, gb.c0 + k);
+    for (int b = 0; b < bw; ++b) { Hd[b * THREADS + tid] = NEG_OE; Fv[b * THREADS + tid] = NEG_OE; }
+
+    for (int n = 0; n < nrows; ++n) {
+      const uint32_t pa = row_profile(va, ga.i_first + n, MM4, MX, N4);
+      const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
+      uint32_t e = NEG_OE, hoe_left = NEG_OE;
+      uint32_t diag = Hd[tid];                                // old Hd[0]
+      uint32_t* hrow = hmine + ((size_t)n * bw) * nthreads;
+      for (int b = 0; b < bw; ++b) {
+        const uint32_t selv = sel[(n + b) * THREADS + tid];
+        uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
+        if (HAS_N) { const uint32_t isn = prmt(selv, 0u, 0xBBAAu); sp = (sp & ~isn) | (POS_OE & isn); }
+        const uint32_t t = __vadd2(diag, sp);
+        uint32_t up_hoe = NEG_OE, up_f = NEG_OE;
+        if (b + 1 < bw) { up_hoe = Hd[(b + 1) * THREADS + tid]; up_f = Fv[(b + 1) * THREADS + tid]; }
+        const uint32_t f = __viaddmax_s16x2(up_f, NEG_EXT, up_hoe);
+        e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);
+        const uint32_t h = __vimax3_s16x2_relu(t, e, f);
+        const uint32_t hoe = __vadd2(h, NEG_OE);
+        hrow[(size_t)b * nthreads] = h;
+        Hd[b * THREADS + tid] = hoe; Fv[b * THREADS + tid] = f; hoe_left = hoe;
+        diag = up_hoe;
+      }
+    }
+    walk_h_and_emit(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * nthreads] & 0xFFFFu); });
+    if (haveB)
+      walk_h_and_emit(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * nthreads] >> 16); });
+  }
+}
+
+// ---- last resort: scalar, band rows + direction bits in global scratch (any width) ----------------
+// Replays the SPEC state machine on stored direction nibbles:
+//   bits 0-1 = H source (0 stop, 1 diagonal, 2 F, 3 E), bit 2 = F came by extension, bit 3 = E came by extension
 // Per-thread scratch, contiguous: [Hs: bw_cap ints][Fs: bw_cap ints][ops: max_rows + 2*bw_cap + 8][dir: max_rows * nw_cap u64]
 __host__ __device__ inline size_t tb_wide_scratch_bytes(int max_rows, int bw_cap) {
   const size_t nw = (size_t)(bw_cap + 15) / 16;
@@ -270,7 +436,6 @@ tb_wide_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
       int hleft = 0, eleft = TB_NEG, hend = -1;
       unsigned long long word = 0ull;
       unsigned long long* drow = dir + (size_t)(i - i_first) * nw;
-      // cells left of bmin are outside the matrix: they keep H = 0, F = -inf from the reset below
       for (int b = 0; b < bmin && b < bw; ++b) { Hs[b] = 0; Fs[b] = TB_NEG; }
       for (int w = 0; w < nw; ++w) drow[w] = 0ull;
       int diagH = (bmin < bw) ? Hs[bmin] : 0;                // H[i-1][j-1] for b = bmin (old value at b)
@@ -295,10 +460,37 @@ tb_wide_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
       if (ie == 0 && i >= i_lo && hend == S) ie = i;
     }
     if (ie == 0) { atomicOr(a.err_flag, 2u); continue; }
-    walk_and_emit(a, task, t, S, ie, je, d_lo, i_first, bw, opbuf,
-                  [&](int row, int b) -> uint32_t {
-                    return (uint32_t)(dir[(size_t)row * nw + b / 16] >> (4 * (b % 16))) & 15u;
-                  });
+    OpRuns o; o.init(opbuf);
+    o.push_run(UBU_SW_CIGAR_S, (uint32_t)(t.L - ie));
+    int i = ie, j = je, state = 0, edits = 0;
+    bool bad = false;
+    while (true) {
+      if (i < 1 || j < 1) { if (state != 0) bad = true; break; }
+      const int b = j - i - d_lo;
+      if (b < 0 || b >= bw || i < i_first) { bad = true; break; }
+      const uint32_t nib = (uint32_t)(dir[(size_t)(i - i_first) * nw + b / 16] >> (4 * (b % 16))) & 15u;
+      if (state == 0) {
+        const uint32_t src = nib & 3u;
+        if (src == 0u) break;
+        if (src == 1u) {
+          o.push(UBU_SW_CIGAR_M, 1u);
+          const uint32_t qc = base2(t.q, (uint32_t)(i - 1)), rc = base2(t.r, (uint32_t)(j - 1));
+          const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1))) || (t.rn && nbit(t.rn, (uint32_t)(j - 1)));
+          if (qc != rc && !isn) ++edits;
+          --i; --j;
+        } else state = (src == 2u) ? 1 : 2;
+      } else if (state == 1) {
+        o.push(UBU_SW_CIGAR_I, 1u); ++edits;
+        --i; if (!(nib & 4u)) state = 0;
+      } else {
+        o.push(UBU_SW_CIGAR_D, 1u); ++edits;
+        --j; if (!(nib & 8u)) state = 0;
+      }
+    }
+    o.flush();
+    o.push_run(UBU_SW_CIGAR_S, (uint32_t)i);
+    if (bad) { atomicOr(a.err_flag, 2u); continue; }
+    emit_result(a, task, o, S, j + 1, je, i + 1, ie, edits);
   }
 }
 

@@ -19,16 +19,18 @@ namespace {
 // ---- length classes of the packed 16-bit forward kernel: rows capacity = G*K -------------------
 struct FwdCfg { int lmax, G, K; };
 constexpr int FWD_THREADS = 64;
-#define UBU_FWD_CFGS(X) X(0, 32, 8, 4) X(1, 48, 8, 6) X(2, 64, 8, 8) X(3, 80, 8, 10) X(4, 96, 8, 12) X(5, 104, 8, 13) \
-  X(6, 128, 8, 16) X(7, 160, 16, 10) X(8, 192, 16, 12) X(9, 208, 16, 13) X(10, 256, 16, 16)
+#define UBU_FWD_CFGS(X) X(0, 32, 4, 8) X(1, 48, 4, 12) X(2, 64, 4, 16) X(3, 76, 4, 19) X(4, 80, 4, 20) X(5, 104, 8, 13) \
+  X(6, 128, 8, 16) X(7, 152, 8, 19) X(8, 160, 8, 20) X(9, 208, 16, 13) X(10, 256, 16, 16)
 #define X(i, l, g, k) {l, g, k},
 const FwdCfg kFwdCfgs[] = {UBU_FWD_CFGS(X)};
 #undef X
 constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
-constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 4;
-constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;
+constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
+constexpr int TBS_THREADS = 32, TBS_GRID_PER_SM = 2;     // shared-memory-band traceback
+constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
+constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
 
 template <class T>
 struct DevBuf {
@@ -70,9 +72,10 @@ struct Slot {
   DevBuf<uint16_t> d_rlen, d_wlen;
   DevBuf<FwdOut> d_fwd;
   DevBuf<ubu_sw_result> d_res;
-  DevBuf<unsigned int> d_ctr;            // [0..2] class counts, [3] cigar cursor, [4] error flags
-  DevBuf<unsigned long long> d_dir;      // direction scratch of the register-band traceback kernels
-  DevBuf<unsigned char> d_wide;          // scratch of the wide-band traceback kernel
+  DevBuf<unsigned int> d_ctr;            // [0..5] class counts, [6] cigar cursor, [7] error flags
+  DevBuf<uint32_t> d_hstore;             // packed H of every band cell (register- and shared-memory-band traceback)
+  DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
+  DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
@@ -81,7 +84,7 @@ struct Slot {
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
   bool any_n = false, have_idx = false, reads_n = false, wins_n = false;
-  int lmax = 0, bw_cap = 0;
+  int lmax = 0, bw_cap = 0, smem_bw_cap = 0;
   unsigned int cig_cap = 0;
   int n_launches = 0;
   // submit()/wait() bookkeeping
@@ -92,7 +95,7 @@ struct Slot {
 
 struct ubu_sw_handle {
   int device = 0, n_slots = 2, sm_count = 148;
-  Scoring sc{1, -3, 5, 2};
+  Scoring sc = make_scoring(1, -3, 5, 2);
   Slot slots[4];
   std::string last_error;
   int next_slot = 0;
@@ -120,13 +123,13 @@ size_t fwd_smem_bytes(int cfg, bool has_n, int wmax) {
   return (size_t)(FWD_THREADS / c.G) * (size_t)sel_stride_for(wmax, c.G) * (has_n ? 4u : 2u);
 }
 
-template <int G, int K, bool HAS_N>
+template <int G, int K, bool HAS_N, bool DEF>
 cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
                          const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
   constexpr int GP = FWD_THREADS / G;
   const int stride = sel_stride_for(L.wmax, G);
   const size_t smem = (size_t)GP * stride * (HAS_N ? 4u : 2u);
-  auto kern = sw_fwd16_kernel<G, K, HAS_N, FWD_THREADS>;
+  auto kern = sw_fwd16_kernel<G, K, HAS_N, DEF, FWD_THREADS>;
   if (smem > 48 * 1024) {      // per device, so set on every large launch (cheap)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return e;
@@ -139,10 +142,13 @@ cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs
 
 cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
                        const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
-  switch (L.cfg * 2 + (L.has_n ? 1 : 0)) {
+  const bool def = sc.match == 1 && sc.mismatch == -3 && sc.gap_open == 5 && sc.gap_ext == 2;
+  switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
 #define X(i, l, g, k) \
-    case i * 2: return launch_fwd_t<g, k, false>(L, reads, wins, idx, order, sc, out, st); \
-    case i * 2 + 1: return launch_fwd_t<g, k, true>(L, reads, wins, idx, order, sc, out, st);
+    case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, st); \
+    case i * 4 + 1: return launch_fwd_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, st); \
+    case i * 4 + 2: return launch_fwd_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, st); \
+    case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, st);
     UBU_FWD_CFGS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -271,14 +277,24 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   CU(h, s.d_cig.reserve(s.cig_cap));
   // traceback scratch
   const int max_rows = std::max(s.lmax, 1);
-  const size_t tb_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
-  CU(h, s.d_dir.reserve(tb_threads * (size_t)max_rows * 2));          // NW = 2 is the widest register class
   {
-    int kmax = 16;
     const int gbmax = gap_bound(h->sc, max_rows, 1);
-    s.bw_cap = std::min(kmax + 2 * gbmax + 1, max_rows + 65535);
-    const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
-    CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
+    s.bw_cap = std::min(kMaxK + 2 * gbmax + 1, max_rows + 65535);
+    // widest band whose rows (Hd, Fv: 2 x u32) and selectors fit the shared-memory kernel
+    const size_t selsz = s.any_n ? 4 : 2;
+    const long avail = (long)kMaxDynSmem - (long)max_rows * TBS_THREADS * (long)selsz;
+    long cap = avail > 0 ? avail / (long)(TBS_THREADS * (8 + selsz)) : 0;
+    s.smem_bw_cap = (int)std::max<long>(0, std::min<long>(cap, s.bw_cap));
+    const size_t reg_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
+    const size_t smem_threads = (size_t)h->sm_count * TBS_GRID_PER_SM * TBS_THREADS;
+    size_t hwords = reg_threads * (size_t)max_rows * 32;                       // BW = 32 is the widest register class
+    if (s.smem_bw_cap > 32) hwords = std::max(hwords, smem_threads * (size_t)max_rows * (size_t)s.smem_bw_cap);
+    CU(h, s.d_hstore.reserve(hwords));
+    CU(h, s.d_ops.reserve(smem_threads * (size_t)(2 * s.smem_bw_cap + max_rows + 8)));
+    if (s.bw_cap > s.smem_bw_cap) {
+      const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
+      CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
+    }
   }
 
   cudaStream_t st = s.stream;
@@ -320,26 +336,61 @@ int do_run(ubu_sw_handle* h, Slot& s) {
 
   TbArgs a;
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
-  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 3; a.err_flag = s.d_ctr.p + 4;
+  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 6; a.err_flag = s.d_ctr.p + 7;
   const int max_rows = std::max(s.lmax, 1);
-  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(s.d_order.p, s.n_slots, s.d_fwd.p, h->sc, s.d_res.p, s.d_lists.p, s.d_ctr.p);
+  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(s.d_order.p, s.n_slots, s.d_fwd.p, h->sc, s.smem_bw_cap, s.d_res.p, s.d_lists.p, s.d_ctr.p);
   CU(h, cudaGetLastError()); ++s.n_launches;
-  const int tb_grid = h->sm_count * TB_GRID_PER_SM;
-  if (s.any_n) {
-    tb_band_kernel<16, true, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0, s.d_dir.p, max_rows);
-    CU(h, cudaGetLastError());
-    tb_band_kernel<32, true, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p + s.n_slots, s.d_ctr.p + 1, s.d_dir.p, max_rows);
-    CU(h, cudaGetLastError());
-  } else {
-    tb_band_kernel<16, false, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0, s.d_dir.p, max_rows);
-    CU(h, cudaGetLastError());
-    tb_band_kernel<32, false, TB_THREADS><<<tb_grid, TB_THREADS, 0, st>>>(a, s.d_lists.p + s.n_slots, s.d_ctr.p + 1, s.d_dir.p, max_rows);
-    CU(h, cudaGetLastError());
+  const size_t NS = s.n_slots;
+  tb_diag_kernel<<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
+  CU(h, cudaGetLastError()); ++s.n_launches;
+  {
+    const int grid = h->sm_count * TB_GRID_PER_SM;
+    const size_t selsz = s.any_n ? 4 : 2;
+    const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
+                 sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
+    if (s.any_n) {
+      auto k8 = tb_fill_reg_kernel<8, true, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, true, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, true, TB_THREADS>;
+      if (sm32 > 48 * 1024) {
+        CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+      }
+      k8<<<grid, TB_THREADS, sm8, st>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, st>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, st>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+    } else {
+      auto k8 = tb_fill_reg_kernel<8, false, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, false, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, false, TB_THREADS>;
+      if (sm32 > 48 * 1024) {
+        CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+      }
+      k8<<<grid, TB_THREADS, sm8, st>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, st>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, st>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+    }
+    s.n_launches += 3;
   }
-  tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, st>>>(a, s.d_lists.p + 2 * (size_t)s.n_slots, s.d_ctr.p + 2,
-                                                                     s.d_wide.p, max_rows, s.bw_cap);
-  CU(h, cudaGetLastError());
-  s.n_launches += 3;
+  if (s.smem_bw_cap > 32) {
+    const size_t selsz = s.any_n ? 4 : 2;
+    const size_t smem = (size_t)s.smem_bw_cap * TBS_THREADS * 8 + (size_t)(max_rows + s.smem_bw_cap) * TBS_THREADS * selsz;
+    const int grid = h->sm_count * TBS_GRID_PER_SM;
+    if (s.any_n) {
+      auto k = tb_fill_smem_kernel<true, TBS_THREADS>;
+      if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+      k<<<grid, TBS_THREADS, smem, st>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, s.d_hstore.p, s.d_ops.p, max_rows, s.smem_bw_cap);
+    } else {
+      auto k = tb_fill_smem_kernel<false, TBS_THREADS>;
+      if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+      k<<<grid, TBS_THREADS, smem, st>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, s.d_hstore.p, s.d_ops.p, max_rows, s.smem_bw_cap);
+    }
+    CU(h, cudaGetLastError()); ++s.n_launches;
+  }
+  if (s.bw_cap > s.smem_bw_cap) {
+    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, st>>>(a, s.d_lists.p + 5 * NS, s.d_ctr.p + 5,
+                                                                       s.d_wide.p, max_rows, s.bw_cap);
+    CU(h, cudaGetLastError()); ++s.n_launches;
+  }
   CU(h, cudaEventRecord(s.ev[2], st));
   s.ran = true;
   return UBU_SW_OK;
@@ -354,7 +405,7 @@ int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size
   for (int attempt = 0;; ++attempt) {
     CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
-    const unsigned int need = s.h_ctr.p[3], err = s.h_ctr.p[4];
+    const unsigned int need = s.h_ctr.p[6], err = s.h_ctr.p[7];
     if (err & 2u) { h->last_error = "internal: traceback left its band (please report)"; return UBU_SW_ERR_CUDA; }
     if (err & 1u) {                    // device CIGAR pool was too small: grow it and redo the device work once
       if (attempt) { h->last_error = "internal: CIGAR pool overflow after regrow"; return UBU_SW_ERR_CUDA; }
@@ -416,7 +467,7 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
   ubu_sw_handle* h = new (std::nothrow) ubu_sw_handle();
   if (!h) return UBU_SW_ERR_NOMEM;
   h->device = device; h->n_slots = slots; h->sm_count = prop.multiProcessorCount;
-  h->sc = Scoring{p.match, p.mismatch, p.gap_open, p.gap_ext};
+  h->sc = make_scoring(p.match, p.mismatch, p.gap_open, p.gap_ext);
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return UBU_SW_ERR_CUDA; }
   for (int i = 0; i < slots; ++i) {
     if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
@@ -436,7 +487,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
     s.d_roff.release(); s.d_rnoff.release(); s.d_woff.release(); s.d_wnoff.release(); s.d_idx.release();
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
-    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_dir.release(); s.d_wide.release();
+    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release();
     s.h_order.release(); s.h_ctr.release();
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.stream) cudaStreamDestroy(s.stream);
