@@ -150,26 +150,46 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
   o.push_run(UBU_SW_CIGAR_S, (uint32_t)(t.L - ie));
   int i = ie, j = g.je, h = g.S, edits = 0;
   bool bad = false;
+  constexpr int WB = 8;                                   // diagonal steps served by one batch of independent loads
   while (h > 0) {
     const int n = i - g.i_first, b = j - i - g.d_lo;
     if (i < 1 || j < 1 || n < 0 || b < 0 || b >= bw) { bad = true; break; }
-    // diagonal
-    const uint32_t qc = base2(t.q, (uint32_t)(i - 1)), rc = base2(t.r, (uint32_t)(j - 1));
-    const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1))) || (t.rn && nbit(t.rn, (uint32_t)(j - 1)));
-    const int s = isn ? 0 : (qc == rc ? ma : mm);
-    const int hdg = (n >= 1 && j >= 2) ? h_at(n - 1, b) : 0;
-    if (hdg + s == h) {
-      o.push(UBU_SW_CIGAR_M, 1u);
-      if (!isn && qc != rc) ++edits;
-      --i; --j; h = hdg;
-      continue;
+    // The next WB cells up this diagonal, fetched together: the walk is latency-bound, and most paths are
+    // long diagonal runs, so one round trip to the H store now serves up to WB steps.
+    int hb[WB], sb[WB]; bool mb[WB];
+#pragma unroll
+    for (int k = 0; k < WB; ++k) {
+      const int ii = i - k, jj = j - k;                   // cell whose diagonal predecessor is wanted
+      hb[k] = (n - k >= 1 && jj >= 2 && ii >= 1) ? h_at(n - k - 1, b) : 0;
+      int s = 0; bool mis = false;
+      if (ii >= 1 && jj >= 1) {
+        const uint32_t qc = base2(t.q, (uint32_t)(ii - 1)), rc = base2(t.r, (uint32_t)(jj - 1));
+        const bool isn = (t.qn && nbit(t.qn, (uint32_t)(ii - 1))) || (t.rn && nbit(t.rn, (uint32_t)(jj - 1)));
+        s = isn ? 0 : (qc == rc ? ma : mm); mis = !isn && qc != rc;
+      }
+      sb[k] = s; mb[k] = mis;
     }
+    bool diag_run = true;
+#pragma unroll
+    for (int k = 0; k < WB; ++k) {
+      if (diag_run && h > 0) {
+        if (i >= 1 && j >= 1 && hb[k] + sb[k] == h) {
+          o.push(UBU_SW_CIGAR_M, 1u);
+          if (mb[k]) ++edits;
+          --i; --j; h = hb[k];
+        } else diag_run = false;
+      }
+    }
+    if (diag_run || h <= 0) continue;                     // batch used up (or finished): fetch the next one
+    // not a diagonal step at (i, j): gaps
+    const int n2 = i - g.i_first, b2 = j - i - g.d_lo;
+    if (i < 1 || j < 1 || n2 < 0 || b2 < 0 || b2 >= bw) { bad = true; break; }
     // read gap (I): largest k with H[i-k][j] - open - k*ext == h
     int kbest = 0;
-    for (int k = 1; k <= n && b + k < bw; ++k) {
-      const int need = h + open + k * ext;              // required H[i-k][j]
+    for (int k = 1; k <= n2 && b2 + k < bw; ++k) {
+      const int need = h + open + k * ext;                // required H[i-k][j]
       if (need > g.S) break;
-      if (h_at(n - k, b + k) == need) kbest = k;
+      if (h_at(n2 - k, b2 + k) == need) kbest = k;
     }
     if (kbest) {
       o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); edits += kbest;
@@ -177,10 +197,10 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
       continue;
     }
     // window gap (D): largest k with H[i][j-k] - open - k*ext == h
-    for (int k = 1; k <= b && j - k >= 1; ++k) {
+    for (int k = 1; k <= b2 && j - k >= 1; ++k) {
       const int need = h + open + k * ext;
       if (need > g.S) break;
-      if (h_at(n, b - k) == need) kbest = k;
+      if (h_at(n2, b2 - k) == need) kbest = k;
     }
     if (kbest) {
       o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); edits += kbest;
@@ -262,7 +282,8 @@ __device__ __forceinline__ uint32_t pair_selector(const TaskView& ta, const Task
 }
 
 // ---- register band fill + walk: one thread = one PAIR of tasks ---------------------------------
-// hstore: packed H of band cell (n, b) of thread gtid at hstore[(n*BW + b) * nthreads + gtid]
+// hstore: one contiguous block per warp, packed H of band cell (n, b) of lane l at block[(n*BW + b) * 32 + l]: a warp's
+//         store is one 128-byte line, consecutive cells are adjacent (streaming writes, TLB-friendly walk reads)
 // selectors: shared memory, sel[k * THREADS + tid], k = n + b
 template <int BW, bool HAS_N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -279,6 +300,7 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
   const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
   uint32_t opbuf[BW + 8];
+  uint32_t* hmine = hstore + (size_t)(gtid >> 5) * ((size_t)max_rows * BW * 32) + (gtid & 31u);
 
   for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
     const uint32_t tA = list[2u * pair];
@@ -299,7 +321,7 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
       const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
       const SelT* srow = sel + (size_t)n * THREADS + tid;
-      uint32_t* hrow = hstore + ((size_t)n * BW) * nthreads + gtid;
+      uint32_t* hrow = hmine + (size_t)n * BW * 32;
 #pragma unroll
       for (int b = 0; b < BW; ++b) {
         const uint32_t selv = srow[b * THREADS];
@@ -311,23 +333,19 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
         e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);                              // E[i][j]
         const uint32_t h = __vimax3_s16x2_relu(t, e, f);
         const uint32_t hoe = __vadd2(h, NEG_OE);
-        hrow[(size_t)b * nthreads] = h;
+        hrow[b * 32] = h;
         Hd[b] = hoe; Fv[b] = f; hoe_left = hoe;
       }
     }
-    walk_h_and_emit(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> int {
-      return (int)(hstore[((size_t)n * BW + b) * nthreads + gtid] & 0xFFFFu);
-    });
+    walk_h_and_emit(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> int { return (int)(hmine[(n * BW + b) * 32] & 0xFFFFu); });
     if (haveB)
-      walk_h_and_emit(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> int {
-        return (int)(hstore[((size_t)n * BW + b) * nthreads + gtid] >> 16);
-      });
+      walk_h_and_emit(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> int { return (int)(hmine[(n * BW + b) * 32] >> 16); });
   }
 }
 
 // ---- shared-memory band fill + walk (any band width up to bw_cap) ---------------------------------
 // shared memory per CTA: Hd[bw_cap][THREADS] u32, Fv[bw_cap][THREADS] u32, sel[(max_rows + bw_cap)][THREADS] SelT
-// hstore: cell (n, b) of thread gtid at hstore[(n * bw + b) * nthreads + gtid]   (bw = this pair's width; n*bw+b < max_rows*bw_cap)
+// hstore: one block of max_rows*bw_cap cells per warp, cell (n, b) of lane l at block[(n * bw + b) * 32 + l] (bw = this pair's width)
 template <bool HAS_N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
@@ -344,7 +362,7 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
   const uint32_t mmb = (uint32_t)(a.sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(a.sc.match + oe) & 0xFFu;
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
   const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
-  uint32_t* hmine = hstore + gtid;
+  uint32_t* hmine = hstore + (size_t)(gtid >> 5) * ((size_t)max_rows * bw_cap * 32) + (gtid & 31u);
   uint32_t* opbuf = opscratch + (size_t)gtid * (size_t)(2 * bw_cap + max_rows + 8);
 
   for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
@@ -366,7 +384,7 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
       const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
       uint32_t diag = Hd[tid];                                // old Hd[0]
-      uint32_t* hrow = hmine + ((size_t)n * bw) * nthreads;
+      uint32_t* hrow = hmine + (size_t)n * bw * 32;
       for (int b = 0; b < bw; ++b) {
         const uint32_t selv = sel[(n + b) * THREADS + tid];
         uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
@@ -378,14 +396,14 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
         e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);
         const uint32_t h = __vimax3_s16x2_relu(t, e, f);
         const uint32_t hoe = __vadd2(h, NEG_OE);
-        hrow[(size_t)b * nthreads] = h;
+        hrow[b * 32] = h;
         Hd[b * THREADS + tid] = hoe; Fv[b * THREADS + tid] = f; hoe_left = hoe;
         diag = up_hoe;
       }
     }
-    walk_h_and_emit(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * nthreads] & 0xFFFFu); });
+    walk_h_and_emit(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * 32] & 0xFFFFu); });
     if (haveB)
-      walk_h_and_emit(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * nthreads] >> 16); });
+      walk_h_and_emit(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * 32] >> 16); });
   }
 }
 

@@ -66,14 +66,17 @@ struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; };
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};    // the traceback classes are independent: they run side by side
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   DevBuf<uint8_t> d_rp, d_rn, d_wp, d_wn;
   DevBuf<uint32_t> d_roff, d_rnoff, d_woff, d_wnoff, d_idx, d_order, d_lists, d_cig;
   DevBuf<uint16_t> d_rlen, d_wlen;
   DevBuf<FwdOut> d_fwd;
   DevBuf<ubu_sw_result> d_res;
   DevBuf<unsigned int> d_ctr;            // [0..5] class counts, [6] cigar cursor, [7] error flags
-  DevBuf<uint32_t> d_hstore;             // packed H of every band cell (register- and shared-memory-band traceback)
+  DevBuf<uint32_t> d_hstore;             // packed H of every band cell: [BW=8 | BW=16 | BW=32 | shared-memory band] regions
+  size_t h_off[4] = {0, 0, 0, 0};
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
@@ -287,8 +290,12 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     s.smem_bw_cap = (int)std::max<long>(0, std::min<long>(cap, s.bw_cap));
     const size_t reg_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
     const size_t smem_threads = (size_t)h->sm_count * TBS_GRID_PER_SM * TBS_THREADS;
-    size_t hwords = reg_threads * (size_t)max_rows * 32;                       // BW = 32 is the widest register class
-    if (s.smem_bw_cap > 32) hwords = std::max(hwords, smem_threads * (size_t)max_rows * (size_t)s.smem_bw_cap);
+    s.h_off[0] = 0;
+    s.h_off[1] = s.h_off[0] + reg_threads * (size_t)max_rows * 8;
+    s.h_off[2] = s.h_off[1] + reg_threads * (size_t)max_rows * 16;
+    s.h_off[3] = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
+    size_t hwords = s.h_off[3];
+    if (s.smem_bw_cap > 32) hwords += smem_threads * (size_t)max_rows * (size_t)s.smem_bw_cap;
     CU(h, s.d_hstore.reserve(hwords));
     CU(h, s.d_ops.reserve(smem_threads * (size_t)(2 * s.smem_bw_cap + max_rows + 8)));
     if (s.bw_cap > s.smem_bw_cap) {
@@ -341,6 +348,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(s.d_order.p, s.n_slots, s.d_fwd.p, h->sc, s.smem_bw_cap, s.d_res.p, s.d_lists.p, s.d_ctr.p);
   CU(h, cudaGetLastError()); ++s.n_launches;
   const size_t NS = s.n_slots;
+  // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
+  CU(h, cudaEventRecord(s.ev_fork, st));
+  for (int k = 0; k < 3; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
   tb_diag_kernel<<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
   CU(h, cudaGetLastError()); ++s.n_launches;
   {
@@ -348,6 +358,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     const size_t selsz = s.any_n ? 4 : 2;
     const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
                  sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
+    uint32_t *h8 = s.d_hstore.p + s.h_off[0], *h16 = s.d_hstore.p + s.h_off[1], *h32 = s.d_hstore.p + s.h_off[2];
     if (s.any_n) {
       auto k8 = tb_fill_reg_kernel<8, true, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, true, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, true, TB_THREADS>;
       if (sm32 > 48 * 1024) {
@@ -355,9 +366,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
         CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
       }
-      k8<<<grid, TB_THREADS, sm8, st>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, st>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, st>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k8<<<grid, TB_THREADS, sm8, s.aux[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, s.aux[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, s.aux[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
     } else {
       auto k8 = tb_fill_reg_kernel<8, false, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, false, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, false, TB_THREADS>;
       if (sm32 > 48 * 1024) {
@@ -365,9 +376,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
         CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
       }
-      k8<<<grid, TB_THREADS, sm8, st>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, st>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, st>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, s.d_hstore.p, max_rows); CU(h, cudaGetLastError());
+      k8<<<grid, TB_THREADS, sm8, s.aux[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, s.aux[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, s.aux[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
     }
     s.n_launches += 3;
   }
@@ -375,21 +386,26 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     const size_t selsz = s.any_n ? 4 : 2;
     const size_t smem = (size_t)s.smem_bw_cap * TBS_THREADS * 8 + (size_t)(max_rows + s.smem_bw_cap) * TBS_THREADS * selsz;
     const int grid = h->sm_count * TBS_GRID_PER_SM;
+    uint32_t* hs = s.d_hstore.p + s.h_off[3];
     if (s.any_n) {
       auto k = tb_fill_smem_kernel<true, TBS_THREADS>;
       if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, st>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, s.d_hstore.p, s.d_ops.p, max_rows, s.smem_bw_cap);
+      k<<<grid, TBS_THREADS, smem, s.aux[2]>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, hs, s.d_ops.p, max_rows, s.smem_bw_cap);
     } else {
       auto k = tb_fill_smem_kernel<false, TBS_THREADS>;
       if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, st>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, s.d_hstore.p, s.d_ops.p, max_rows, s.smem_bw_cap);
+      k<<<grid, TBS_THREADS, smem, s.aux[2]>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, hs, s.d_ops.p, max_rows, s.smem_bw_cap);
     }
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
   if (s.bw_cap > s.smem_bw_cap) {
-    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, st>>>(a, s.d_lists.p + 5 * NS, s.d_ctr.p + 5,
-                                                                       s.d_wide.p, max_rows, s.bw_cap);
+    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[2]>>>(a, s.d_lists.p + 5 * NS, s.d_ctr.p + 5,
+                                                                              s.d_wide.p, max_rows, s.bw_cap);
     CU(h, cudaGetLastError()); ++s.n_launches;
+  }
+  for (int k = 0; k < 3; ++k) {                       // join
+    CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
+    CU(h, cudaStreamWaitEvent(st, s.ev_join[k], 0));
   }
   CU(h, cudaEventRecord(s.ev[2], st));
   s.ran = true;
@@ -473,6 +489,11 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
     if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     for (int e = 0; e < 3; ++e)
       if (cudaEventCreate(&h->slots[i].ev[e]) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&h->slots[i].ev_fork, cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    for (int e = 0; e < 3; ++e) {
+      if (cudaStreamCreateWithFlags(&h->slots[i].aux[e], cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+      if (cudaEventCreateWithFlags(&h->slots[i].ev_join[e], cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    }
   }
   *out = h;
   return UBU_SW_OK;
@@ -490,6 +511,8 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release();
     s.h_order.release(); s.h_ctr.release();
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    for (int e = 0; e < 3; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   delete h;
