@@ -1,0 +1,182 @@
+"""Multi-GPU use of the path: reads shard trivially, so there is NO collective on the data path.
+
+The reference already treats its two input BAMs and its regions as independent work
+(src/main/java/edu/unc/bioinf/ubu/assembly/ReAligner.java:180-184,199-200,328-349) and hands parallelism to
+`bwa -t N` (Aligner.java:19,49). Here the batch is cut into fixed-size chunks in input order; chunk c belongs to
+rank c mod world (round-robin keeps mixed-length inputs balanced); every rank aligns its chunks on its own GPU
+through its own stream pipeline (ubu_sw_submit / ubu_sw_wait); an ordered merge releases chunk c only after c-1,
+so records come out in input order. Two drivers share that logic:
+
+  * MultiGpuAligner  -- one process, one host thread + one handle per GPU (library use);
+  * align_rank / merge_ordered -- one process per GPU (torchrun); torch.distributed is used only to gather the
+    per-rank results to rank 0, never inside the alignment.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .aligner import RESULT_DTYPE, Alignments
+from .seqs import SeqSet
+
+
+@dataclass(frozen=True)
+class Chunk:
+    cid: int
+    lo: int
+    hi: int
+    rank: int
+
+
+def plan_chunks(n_tasks: int, chunk: int, world: int) -> List[Chunk]:
+    """Input-order chunks, chunk c -> rank c % world."""
+    if chunk <= 0 or world <= 0:
+        raise ValueError("chunk and world must be positive")
+    return [Chunk(c, lo, min(lo + chunk, n_tasks), c % world) for c, lo in enumerate(range(0, n_tasks, chunk))]
+
+
+def window_slice(windows: SeqSet, idx: Optional[np.ndarray], lo: int, hi: int) -> Tuple[SeqSet, Optional[np.ndarray]]:
+    """Windows a chunk of reads needs, re-indexed from 0 when they form a contiguous range (the common layout:
+    reads grouped by window); otherwise the whole window set is kept."""
+    if idx is None:
+        return windows.slice(lo, hi), None
+    part = idx[lo:hi]
+    if part.size == 0:
+        return windows.slice(0, 0), part
+    w0, w1 = int(part.min()), int(part.max()) + 1
+    if w1 - w0 <= 2 * (hi - lo) + 16:
+        return windows.slice(w0, w1), (part - np.uint32(w0)).astype(np.uint32)
+    return windows, part
+
+
+class OrderedMerger:
+    """Reorder buffer: push(cid, payload) in any order, pop_ready() yields payloads in chunk order."""
+
+    def __init__(self, n_chunks: int):
+        self.n, self.next, self.held = n_chunks, 0, {}  # type: int, int, Dict[int, object]
+        self.lock = threading.Lock()
+
+    def push(self, cid: int, payload) -> None:
+        with self.lock:
+            if cid in self.held or cid < self.next or cid >= self.n:
+                raise ValueError(f"chunk {cid} pushed twice or out of range")
+            self.held[cid] = payload
+
+    def pop_ready(self) -> Iterator[Tuple[int, object]]:
+        while True:
+            with self.lock:
+                if self.next not in self.held:
+                    return
+                cid, payload = self.next, self.held.pop(self.next)
+                self.next += 1
+            yield cid, payload
+
+    @property
+    def done(self) -> bool:
+        return self.next == self.n
+
+
+def merge_ordered(n_tasks: int, parts: Sequence[Tuple[Chunk, np.ndarray, np.ndarray]]) -> Alignments:
+    """Concatenates per-chunk (results, cigar ops) in input order, rebasing cigar_off into one pool."""
+    res = np.zeros(n_tasks, dtype=RESULT_DTYPE)
+    pools, base = [], 0
+    seen = 0
+    for ch, r, pool in sorted(parts, key=lambda p: p[0].cid):
+        if ch.lo != seen:
+            raise ValueError("chunks do not tile the input")
+        seen = ch.hi
+        r = r.copy()
+        r["cigar_off"] = (r["cigar_off"].astype(np.int64) + base).astype(np.uint32)
+        res[ch.lo:ch.hi] = r
+        pools.append(pool)
+        base += int(pool.shape[0])
+    if seen != n_tasks:
+        raise ValueError("chunks do not cover the input")
+    return Alignments(res, np.concatenate(pools) if pools else np.zeros(0, np.uint32))
+
+
+AlignFn = Callable[[SeqSet, SeqSet, Optional[np.ndarray]], Alignments]
+
+
+def align_rank(reads: SeqSet, windows: SeqSet, idx: Optional[np.ndarray], rank: int, world: int, chunk: int,
+               align_fn: AlignFn) -> List[Tuple[Chunk, np.ndarray, np.ndarray]]:
+    """This rank's share: its chunks, aligned one after the other with align_fn (SwAligner.align on a GPU box)."""
+    out = []
+    for ch in plan_chunks(reads.count, chunk, world):
+        if ch.rank != rank:
+            continue
+        w, ix = window_slice(windows, idx, ch.lo, ch.hi)
+        al = align_fn(reads.slice(ch.lo, ch.hi), w, ix)
+        out.append((ch, al.results, al.cigar_pool))
+    return out
+
+
+def gather_to_rank0(parts, n_tasks: int, dist=None) -> Optional[Alignments]:
+    """One process per GPU: collect every rank's chunks on rank 0 and merge them in input order."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return merge_ordered(n_tasks, parts)
+    gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(parts, gathered, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    return merge_ordered(n_tasks, [p for rank_parts in gathered for p in rank_parts])
+
+
+class MultiGpuAligner:
+    """One process driving several GPUs: a host thread and a SwAligner handle per device, chunks dealt round-robin,
+    results merged in input order as they complete."""
+
+    def __init__(self, devices: Sequence[int], chunk: int = 250_000, aligner_factory=None, **params):
+        from .aligner import SwAligner
+
+        make = aligner_factory or (lambda dev: SwAligner(device=dev, slots=3, **params))
+        self.devices, self.chunk = list(devices), chunk
+        self.aligners = [make(d) for d in self.devices]
+
+    def close(self) -> None:
+        for a in self.aligners:
+            if hasattr(a, "close"):
+                a.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def align(self, reads: SeqSet, windows: SeqSet, idx: Optional[np.ndarray] = None) -> Alignments:
+        world = len(self.aligners)
+        chunks = plan_chunks(reads.count, self.chunk, world)
+        merger = OrderedMerger(len(chunks))
+        parts, errors = [], []
+
+        def work(rank: int):
+            try:
+                al = self.aligners[rank]
+                for ch in chunks:
+                    if ch.rank != rank:
+                        continue
+                    w, ix = window_slice(windows, idx, ch.lo, ch.hi)
+                    r = al.align(reads.slice(ch.lo, ch.hi), w, ix)
+                    merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+            except Exception as e:  # surfaced on the calling thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        alive = True
+        while alive:
+            alive = any(t.is_alive() for t in threads)
+            for _, p in merger.pop_ready():
+                parts.append(p)
+            if alive:
+                threads[0].join(timeout=0.005)
+        for _, p in merger.pop_ready():
+            parts.append(p)
+        if errors:
+            raise errors[0]
+        return merge_ordered(reads.count, parts)
