@@ -33,7 +33,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, SRC]
+    extra = os.environ.get("UBU_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -38,8 +38,14 @@ namespace ubu {
 // DEFAULT_SC = true compiles SPEC.md's default scoring (+1/-3/5/2) in as immediates: the packed
 // instructions then read two registers instead of three, which matters because the register file,
 // not just the ALU pipe, limits the dual-pipe issue rate (bench/rf_probe.cu).
+#ifndef UBU_FWD_MIN_BLOCKS
+#define UBU_FWD_MIN_BLOCKS 1
+#endif
+#ifndef UBU_FWD_UNROLL
+#define UBU_FWD_UNROLL 2
+#endif
 template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, UBU_FWD_MIN_BLOCKS)
 sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
                 const uint32_t* __restrict__ order, uint32_t n_slots, Scoring sc,
                 FwdOut* __restrict__ out, int sel_stride) {
@@ -131,7 +137,8 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
   const uint32_t badd = (g == 0) ? NEG_OE : 0u;
   asm volatile("" : "+r"(bmul));                          // opaque, so the multiply is not folded back into a select
 
-#pragma unroll 1
+  constexpr int STEP_UNROLL = UBU_FWD_UNROLL;
+#pragma unroll STEP_UNROLL
   for (int s = 0; s < nsteps; ++s) {
     const uint32_t selv = selp[s];
     const uint32_t up = __shfl_up_sync(0xffffffffu, hoe_bot, 1, G) * bmul + badd;   // row 0: H[0][j] = 0

@@ -49,12 +49,13 @@ struct TbArgs {
 
 // Band geometry of one task (SPEC.md section 7).
 struct Band {
-  int S, je, i_lo, i_hi, d_lo, bw, i_first, rows, c0;
+  int S, je, i_lo, i_hi, d_lo, bw, i_first, rows, c0, gb;
 };
 __host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdOut& f, int bw_fixed) {
   Band g;
   g.S = f.score; g.je = f.je; g.i_lo = f.i_lo; g.i_hi = f.i_hi;
   const int Gb = gap_bound(sc, f.i_hi, f.score);
+  g.gb = Gb;
   g.d_lo = f.je - f.i_hi - Gb;
   g.bw = bw_fixed > 0 ? bw_fixed : (f.i_hi - f.i_lo) + 2 * Gb + 1;
   g.i_first = 2 - g.d_lo - g.bw; if (g.i_first < 1) g.i_first = 1;     // first row whose band touches column 1
@@ -148,7 +149,7 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
   if (ie == 0) { atomicOr(a.err_flag, 2u); return; }
   OpRuns o; o.init(opbuf);
   o.push_run(UBU_SW_CIGAR_S, (uint32_t)(t.L - ie));
-  int i = ie, j = g.je, h = g.S, edits = 0;
+  int i = ie, j = g.je, h = g.S, edits = 0, grem = gap_bound(a.sc, ie, g.S);   // gap bases still affordable
   bool bad = false;
   constexpr int WB = 8;                                   // diagonal steps served by one batch of independent loads
   while (h > 0) {
@@ -184,26 +185,39 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
     // not a diagonal step at (i, j): gaps
     const int n2 = i - g.i_first, b2 = j - i - g.d_lo;
     if (i < 1 || j < 1 || n2 < 0 || b2 < 0 || b2 >= bw) { bad = true; break; }
+    // Gap runs are bounded three ways: the band, the gap budget of SPEC section 7 (what is left of it), and
+    // need <= S. Candidates are fetched in batches of independent loads (the scan is latency-bound too).
+    const int kcap = min(grem, (g.S - h - open) / ext);
     // read gap (I): largest k with H[i-k][j] - open - k*ext == h
     int kbest = 0;
-    for (int k = 1; k <= n2 && b2 + k < bw; ++k) {
-      const int need = h + open + k * ext;                // required H[i-k][j]
-      if (need > g.S) break;
-      if (h_at(n2 - k, b2 + k) == need) kbest = k;
+    {
+      const int kmax = min(kcap, min(n2, bw - 1 - b2));
+      for (int k0 = 1; k0 <= kmax; k0 += WB) {
+        int hv[WB];
+#pragma unroll
+        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? h_at(n2 - k0 - u, b2 + k0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
+      }
     }
     if (kbest) {
-      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); edits += kbest;
+      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); edits += kbest; grem -= kbest;
       i -= kbest; h += open + kbest * ext;
       continue;
     }
     // window gap (D): largest k with H[i][j-k] - open - k*ext == h
-    for (int k = 1; k <= b2 && j - k >= 1; ++k) {
-      const int need = h + open + k * ext;
-      if (need > g.S) break;
-      if (h_at(n2, b2 - k) == need) kbest = k;
+    {
+      const int kmax = min(kcap, min(b2, j - 1));
+      for (int k0 = 1; k0 <= kmax; k0 += WB) {
+        int hv[WB];
+#pragma unroll
+        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? h_at(n2, b2 - k0 - u) : -1;
+#pragma unroll
+        for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
+      }
     }
     if (kbest) {
-      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); edits += kbest;
+      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); edits += kbest; grem -= kbest;
       j -= kbest; h += open + kbest * ext;
       continue;
     }
