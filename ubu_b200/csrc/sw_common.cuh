@@ -50,6 +50,29 @@ __device__ __forceinline__ uint32_t pack16x2(int v) {
   return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16);
 }
 
+// 16 consecutive bases (2 bits each, base `start` in bits 0-1) of a byte-aligned 2-bit sequence. `start` may be
+// negative: bases before the sequence come back as zeros in the low positions (callers mask them by range).
+// Reads at most 7 bytes past the last needed base: every packed buffer is uploaded with 16 bytes of slack.
+__device__ __forceinline__ uint32_t load16(const uint8_t* __restrict__ seq, int start) {
+  const int adj = start < 0 ? -start : 0;                    // bases to skip at the front
+  const int s0 = start + adj;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(seq) + (uintptr_t)(s0 >> 2);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(addr & 3u) * 8u + (uint32_t)(s0 & 3) * 2u;
+  const uint32_t v = __funnelshift_r(w[0], w[1], sh);
+  return adj >= 16 ? 0u : (v << (2 * adj));
+}
+// 16 consecutive N-plane bits (bit `start` in bit 0); same conventions.
+__device__ __forceinline__ uint32_t load16n(const uint8_t* __restrict__ nm, int start) {
+  const int adj = start < 0 ? -start : 0;
+  const int s0 = start + adj;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(nm) + (uintptr_t)(s0 >> 3);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(addr & 3u) * 8u + (uint32_t)(s0 & 7);
+  const uint32_t v = __funnelshift_r(w[0], w[1], sh) & 0xFFFFu;
+  return adj >= 16 ? 0u : ((v << adj) & 0xFFFFu);
+}
+
 // prmt.b32 in its default mode: selector nibble bit 3 set = replicate the selected byte's sign bit.
 // (Inline PTX rather than __byte_perm, whose documented contract only covers selector bits 2:0.)
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {

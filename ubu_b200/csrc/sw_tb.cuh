@@ -5,15 +5,15 @@
 // diagonal band  d = j - i  in  [je - i_hi - Gb, je - i_lo + Gb],  Gb = gap_bound(i_hi, S).
 //
 // FILL. The band is re-filled with the same packed 16-bit arithmetic as the forward pass, two tasks
-// per thread (task A in the low, task B in the high half), one band row per loop trip; only H is
-// stored (one packed word per band cell). Cells left of column 1 see padding selectors (score <= 0
+// per thread (task A in the low, task B in the high half), one band row per loop trip; per cell one 16-bit
+// value per task is stored: H in bits 0-14 and, in bit 15, "the diagonal does NOT reproduce H" (h != Hdiag + s). Cells left of column 1 see padding selectors (score <= 0
 // after bias), so they evaluate to H = 0, E = F = -oe, which is what the matrix boundary needs;
 // cells right of column je only feed cells right of column je. Banded values are <= the full-matrix
 // values everywhere and equal on the SPEC path.
 //
-// WALK. The SPEC state machine is replayed from stored H values alone:
+// WALK. The SPEC state machine is replayed from the stored values alone (no sequence access on the way):
 //   * stop when the running score reaches 0 (H along the path is the running score);
-//   * diagonal first:  H[i-1][j-1] + s(q_i, r_j) == H[i][j];
+//   * diagonal first:  H[i-1][j-1] + s(q_i, r_j) == H[i][j]  (the stored flag);
 //   * else read-gap (I) if some k has H[i-k][j] - open - k*ext == H[i][j]; SPEC's "extension preferred
 //     over gap-close" picks the LARGEST such k (an extension step at row x exists iff some k' >= 2
 //     reproduces the value from row x, so the chain runs to the farthest opener);
@@ -135,104 +135,116 @@ __device__ __forceinline__ void emit_result(const TbArgs& a, uint32_t task, cons
   a.res[task] = r;
 }
 
-// Walk on stored H values (see the header comment). HAt(n, b) returns H of band cell b in band row n
-// (n = i - i_first) for THIS task's half; rows above i_first / columns left of 1 are the zero boundary.
-template <class HAt>
+// Walk on the stored band values (see the header comment). WordAt(n, b) returns the 16-bit value of band cell b in
+// band row n (n = i - i_first) for THIS task's half: bits 0-14 = H, bit 15 = diagonal does not reproduce H.
+// Rows above i_first are the zero boundary; cells left of column 1 were filled as H = 0.
+template <bool HAS_N, class WordAt>
 __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, const TaskView& t, const Band& g, int bw,
-                                                uint32_t* opbuf, HAt h_at) {
+                                                uint32_t* opbuf, WordAt word_at) {
   const int ma = a.sc.match, mm = a.sc.mismatch, open = a.sc.gap_open, ext = a.sc.gap_ext;
+  constexpr int WB = 8;                                   // cells served by one batch of independent loads
   // SPEC section 4: smallest row among the candidates that reaches S in column je
   int ie = 0;
-  for (int i = g.i_lo; i <= g.i_hi; ++i) {
-    if (h_at(i - g.i_first, g.je - i - g.d_lo) == g.S) { ie = i; break; }
+  for (int i0 = g.i_lo; i0 <= g.i_hi && !ie; i0 += WB) {
+    int v[WB];
+#pragma unroll
+    for (int u = 0; u < WB; ++u) v[u] = (i0 + u <= g.i_hi) ? (int)(word_at(i0 + u - g.i_first, g.je - i0 - u - g.d_lo) & 0x7FFFu) : -1;
+#pragma unroll
+    for (int u = WB - 1; u >= 0; --u) if (v[u] == g.S) ie = i0 + u;
   }
   if (ie == 0) { atomicOr(a.err_flag, 2u); return; }
   OpRuns o; o.init(opbuf);
   o.push_run(UBU_SW_CIGAR_S, (uint32_t)(t.L - ie));
-  int i = ie, j = g.je, h = g.S, edits = 0, grem = gap_bound(a.sc, ie, g.S);   // gap bases still affordable
+  int i = ie, j = g.je, h = g.S, n_m = 0, gap_bases = 0, gap_cost = 0, grem = gap_bound(a.sc, ie, g.S);
   bool bad = false;
-  constexpr int WB = 8;                                   // diagonal steps served by one batch of independent loads
   while (h > 0) {
     const int n = i - g.i_first, b = j - i - g.d_lo;
     if (i < 1 || j < 1 || n < 0 || b < 0 || b >= bw) { bad = true; break; }
-    // The next WB cells up this diagonal, fetched together: the walk is latency-bound, and most paths are
-    // long diagonal runs, so one round trip to the H store now serves up to WB steps.
-    int hb[WB], sb[WB]; bool mb[WB];
+    // this cell and the next WB up its diagonal, fetched together: the walk is latency-bound and most paths are
+    // long diagonal runs, so one round trip to the H store serves up to WB steps
+    uint32_t w[WB + 1];
+#pragma unroll
+    for (int k = 0; k <= WB; ++k) w[k] = (n - k >= 0) ? word_at(n - k, b) : 0u;
+    bool stop = false;
 #pragma unroll
     for (int k = 0; k < WB; ++k) {
-      const int ii = i - k, jj = j - k;                   // cell whose diagonal predecessor is wanted
-      hb[k] = (n - k >= 1 && jj >= 2 && ii >= 1) ? h_at(n - k - 1, b) : 0;
-      int s = 0; bool mis = false;
-      if (ii >= 1 && jj >= 1) {
-        const uint32_t qc = base2(t.q, (uint32_t)(ii - 1)), rc = base2(t.r, (uint32_t)(jj - 1));
-        const bool isn = (t.qn && nbit(t.qn, (uint32_t)(ii - 1))) || (t.rn && nbit(t.rn, (uint32_t)(jj - 1)));
-        s = isn ? 0 : (qc == rc ? ma : mm); mis = !isn && qc != rc;
-      }
-      sb[k] = s; mb[k] = mis;
-    }
-    bool diag_run = true;
-#pragma unroll
-    for (int k = 0; k < WB; ++k) {
-      if (diag_run && h > 0) {
-        if (i >= 1 && j >= 1 && hb[k] + sb[k] == h) {
-          o.push(UBU_SW_CIGAR_M, 1u);
-          if (mb[k]) ++edits;
-          --i; --j; h = hb[k];
-        } else diag_run = false;
+      if (!stop) {
+        if (h > 0 && !(w[k] & 0x8000u)) { o.push(UBU_SW_CIGAR_M, 1u); ++n_m; --i; --j; h = (int)(w[k + 1] & 0x7FFFu); }
+        else stop = true;
       }
     }
-    if (diag_run || h <= 0) continue;                     // batch used up (or finished): fetch the next one
-    // not a diagonal step at (i, j): gaps
+    if (!stop || h <= 0) continue;
+    // (i, j) is not entered diagonally: a gap run. Runs are bounded by the band, by what is left of the SPEC
+    // section 7 gap budget, and by need <= S; candidates are fetched in batches of independent loads.
     const int n2 = i - g.i_first, b2 = j - i - g.d_lo;
     if (i < 1 || j < 1 || n2 < 0 || b2 < 0 || b2 >= bw) { bad = true; break; }
-    // Gap runs are bounded three ways: the band, the gap budget of SPEC section 7 (what is left of it), and
-    // need <= S. Candidates are fetched in batches of independent loads (the scan is latency-bound too).
     const int kcap = min(grem, (g.S - h - open) / ext);
-    // read gap (I): largest k with H[i-k][j] - open - k*ext == h
     int kbest = 0;
-    {
+    {   // read gap (I): largest k with H[i-k][j] - open - k*ext == h
       const int kmax = min(kcap, min(n2, bw - 1 - b2));
       for (int k0 = 1; k0 <= kmax; k0 += WB) {
         int hv[WB];
 #pragma unroll
-        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? h_at(n2 - k0 - u, b2 + k0 + u) : -1;
+        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? (int)(word_at(n2 - k0 - u, b2 + k0 + u) & 0x7FFFu) : -1;
 #pragma unroll
         for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
       }
     }
     if (kbest) {
-      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); edits += kbest; grem -= kbest;
+      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); gap_bases += kbest; gap_cost += open + kbest * ext; grem -= kbest;
       i -= kbest; h += open + kbest * ext;
       continue;
     }
-    // window gap (D): largest k with H[i][j-k] - open - k*ext == h
-    {
+    {   // window gap (D): largest k with H[i][j-k] - open - k*ext == h
       const int kmax = min(kcap, min(b2, j - 1));
       for (int k0 = 1; k0 <= kmax; k0 += WB) {
         int hv[WB];
 #pragma unroll
-        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? h_at(n2, b2 - k0 - u) : -1;
+        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? (int)(word_at(n2, b2 - k0 - u) & 0x7FFFu) : -1;
 #pragma unroll
         for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
       }
     }
     if (kbest) {
-      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); edits += kbest; grem -= kbest;
+      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); gap_bases += kbest; gap_cost += open + kbest * ext; grem -= kbest;
       j -= kbest; h += open + kbest * ext;
       continue;
     }
     bad = true; break;
   }
   o.flush();
-  o.push_run(UBU_SW_CIGAR_S, (uint32_t)i);     // q_start - 1 = i
   if (bad) { atomicOr(a.err_flag, 2u); return; }
-  emit_result(a, task, o, g.S, j + 1, g.je, i + 1, ie, edits);
+  // edit distance = mismatching M columns + gap bases (SPEC section 6)
+  int mism;
+  if (!HAS_N || (!t.qn && !t.rn)) {
+    // without N every M column scores match or mismatch: S = ma*(n_m - x) + mm*x - gap_cost
+    const int num = ma * n_m - gap_cost - g.S;
+    mism = num / (ma - mm);
+    if (num < 0 || mism * (ma - mm) != num) { atomicOr(a.err_flag, 2u); return; }
+  } else {
+    mism = 0;                                               // replay the runs front to back against the sequences
+    int qi = i, rj = j;                                     // 0-based positions of the first aligned bases
+    for (int k = o.n - 1; k >= 0; --k) {
+      const int len = (int)(o.ops[k] >> 4); const uint32_t op = o.ops[k] & 15u;
+      if (op == UBU_SW_CIGAR_M) {
+        for (int u = 0; u < len; ++u) {
+          const bool isn = (t.qn && nbit(t.qn, (uint32_t)(qi + u))) || (t.rn && nbit(t.rn, (uint32_t)(rj + u)));
+          if (!isn && base2(t.q, (uint32_t)(qi + u)) != base2(t.r, (uint32_t)(rj + u))) ++mism;
+        }
+        qi += len; rj += len;
+      } else if (op == UBU_SW_CIGAR_I) qi += len;
+      else if (op == UBU_SW_CIGAR_D) rj += len;
+    }
+  }
+  o.push_run(UBU_SW_CIGAR_S, (uint32_t)i);     // q_start - 1 = i
+  emit_result(a, task, o, g.S, j + 1, g.je, i + 1, ie, mism + gap_bases);
 }
 
 // ---- class 0: no gap fits under the score (Gb == 0) ---------------------------------------------
 // Every path of score S ending in a candidate cell is gap-free, so H[i][je] == S iff the best purely
 // diagonal local score ending there is S, and the SPEC walk is the diagonal itself: accumulate scores
 // backwards from (i, je); the first time the sum reaches S the running H hits 0 (SPEC stop).
+template <bool HAS_N>
 __global__ void __launch_bounds__(128)
 tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count) {
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,14 +259,27 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
     for (int i = f.i_lo; i <= f.i_hi && !ie; ++i) {
       const int maxk = min(i, je);
       int run = 0, mism = 0;
-      for (int k = 0; k < maxk; ++k) {
-        const uint32_t qc = base2(t.q, (uint32_t)(i - 1 - k)), rc = base2(t.r, (uint32_t)(je - 1 - k));
-        const bool isn = (t.qn && nbit(t.qn, (uint32_t)(i - 1 - k))) || (t.rn && nbit(t.rn, (uint32_t)(je - 1 - k)));
-        const bool eq = qc == rc;
-        run += isn ? 0 : (eq ? ma : mm);
-        mism += (!isn && !eq) ? 1 : 0;
-        if (run == S) { ie = i; len = k + 1; edits = mism; break; }
-        if (run + (maxk - 1 - k) * ma < S) break;            // S is out of reach on this diagonal
+      bool done = false;
+      for (int k0 = 0; k0 < maxk && !done; k0 += 16) {
+        // 16 bases of the read ending at row i-k0 and of the window ending at column je-k0; base k0+15-u sits at bits 2u
+        const uint32_t x = load16(t.q, i - 16 - k0) ^ load16(t.r, je - 16 - k0);
+        uint32_t nm = 0u;
+        if (HAS_N) {
+          if (t.qn) nm |= load16n(t.qn, i - 16 - k0);
+          if (t.rn) nm |= load16n(t.rn, je - 16 - k0);
+        }
+#pragma unroll
+        for (int u = 15; u >= 0; --u) {
+          const int k = k0 + 15 - u;
+          if (!done && k < maxk) {
+            const bool diff = ((x >> (2 * u)) & 3u) != 0u;
+            const bool isn = HAS_N && ((nm >> u) & 1u);
+            run += isn ? 0 : (diff ? mm : ma);
+            mism += (!isn && diff) ? 1 : 0;
+            if (run == S) { ie = i; len = k + 1; edits = mism; done = true; }
+            else if (run + (maxk - 1 - k) * ma < S) done = true;           // S is out of reach on this diagonal
+          }
+        }
       }
     }
     if (!ie) { atomicOr(a.err_flag, 2u); continue; }
@@ -273,30 +298,70 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
   }
 }
 
-// Per-row byte profile of one read base (same encoding as the forward pass).
-__device__ __forceinline__ uint32_t row_profile(const TaskView& t, int i /*1-based*/, uint32_t MM4, uint32_t MX, uint32_t N4) {
-  if (i < 1 || i > t.L) return 0x80808080u;
-  if (t.qn && nbit(t.qn, (uint32_t)(i - 1))) return N4;
-  return MM4 ^ (MX << (8u * base2(t.q, (uint32_t)(i - 1))));
+// ---- pieces shared by the packed fill kernels ---------------------------------------------------
+// Byte profile of read base `code` (same encoding as the forward pass).
+__device__ __forceinline__ uint32_t profile_of(uint32_t code, bool isn, bool valid, uint32_t MM4, uint32_t MX, uint32_t N4) {
+  return !valid ? 0x80808080u : (isn ? N4 : (MM4 ^ (MX << (8u * code))));
 }
 
-// Selector of band column k (0-based window columns cA, cB) for the pair; padding outside [0, W).
+// Streams the read bases of band rows n = 0, 1, ... (row n is read row i_first + n), 16 rows per 32-bit load.
+struct RowCodes {
+  const TaskView* t; int i_first; uint32_t w, nw;
+  __device__ __forceinline__ void init(const TaskView* tv, int ifirst) { t = tv; i_first = ifirst; w = 0u; nw = 0u; }
+  template <bool HAS_N>
+  __device__ __forceinline__ uint32_t profile(int n, uint32_t MM4, uint32_t MX, uint32_t N4) {
+    const int i0 = i_first - 1 + n;                        // 0-based read position of row n
+    if ((n & 15) == 0) {
+      const bool any = i0 < t->L;
+      w = any ? load16(t->q, i0) : 0u;
+      nw = (HAS_N && t->qn && any) ? load16n(t->qn, i0) : 0u;
+    }
+    const int u = n & 15;
+    return profile_of((w >> (2 * u)) & 3u, (nw >> u) & 1u, i0 < t->L, MM4, MX, N4);
+  }
+};
+
+// Selectors of band columns k = 0 .. ncols-1 (0-based window columns c0A + k / c0B + k) for the pair, 16 per pair of
+// 32-bit loads; columns outside [0, W) get the padding selector (score <= 0 after bias).
+template <bool HAS_N, class Store>
+__device__ __forceinline__ void build_selectors(const TaskView& ta, const TaskView& tb, int c0A, int c0B, int ncols, Store store) {
+  for (int k0 = 0; k0 < ncols; k0 += 16) {
+    const int ca = c0A + k0, cb = c0B + k0;
+    const bool anyA = ca < ta.W && ca + 16 > 0, anyB = cb < tb.W && cb + 16 > 0;
+    const uint32_t wa = anyA ? load16(ta.r, ca) : 0u, wb = anyB ? load16(tb.r, cb) : 0u;
+    uint32_t na = 0u, nb = 0u;
+    if (HAS_N) { if (ta.rn && anyA) na = load16n(ta.rn, ca); if (tb.rn && anyB) nb = load16n(tb.rn, cb); }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (k0 + u < ncols) {
+        uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;
+        if (ca + u >= 0 && ca + u < ta.W) { const uint32_t c = (wa >> (2 * u)) & 3u; lo = c | ((c | 8u) << 4); if (HAS_N && ((na >> u) & 1u)) nf |= 0x00800000u; }
+        if (cb + u >= 0 && cb + u < tb.W) { const uint32_t c = ((wb >> (2 * u)) & 3u) + 4u; hi = c | ((c | 8u) << 4); if (HAS_N && ((nb >> u) & 1u)) nf |= 0x80000000u; }
+        store(k0 + u, lo | (hi << 8) | nf);
+      }
+    }
+  }
+}
+
+// One packed band cell. Returns the value to store: H | (diagonal does not reproduce H) << 15, per half.
 template <bool HAS_N>
-__device__ __forceinline__ uint32_t pair_selector(const TaskView& ta, const TaskView& tb, int cA, int cB) {
-  uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;
-  if (cA >= 0 && cA < ta.W) {
-    const uint32_t b = base2(ta.r, (uint32_t)cA); lo = b | ((b | 8u) << 4);
-    if (HAS_N && ta.rn && nbit(ta.rn, (uint32_t)cA)) nf |= 0x00800000u;
-  }
-  if (cB >= 0 && cB < tb.W) {
-    const uint32_t b = base2(tb.r, (uint32_t)cB) + 4u; hi = b | ((b | 8u) << 4);
-    if (HAS_N && tb.rn && nbit(tb.rn, (uint32_t)cB)) nf |= 0x80000000u;
-  }
-  return lo | (hi << 8) | nf;
+__device__ __forceinline__ uint32_t band_cell(uint32_t pa, uint32_t pb, uint32_t selv, uint32_t diag_hoe, uint32_t up_hoe, uint32_t up_f,
+                                              uint32_t& e, uint32_t& hoe_left, uint32_t& f_out, uint32_t NEG_OE, uint32_t NEG_EXT,
+                                              uint32_t POS_OE) {
+  uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
+  if (HAS_N) { const uint32_t isn = prmt(selv, 0u, 0xBBAAu); sp = (sp & ~isn) | (POS_OE & isn); }
+  const uint32_t t = __vadd2(diag_hoe, sp);                                 // H[i-1][j-1] + s
+  const uint32_t f = __viaddmax_s16x2(up_f, NEG_EXT, up_hoe);               // F[i][j]
+  e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);                               // E[i][j]
+  const uint32_t h = __vimax3_s16x2_relu(t, e, f);
+  hoe_left = __vadd2(h, NEG_OE);
+  f_out = f;
+  const uint32_t notdiag = __vmins2(__vsub2(h, t), 0x00010001u);           // h >= t always: 0 iff the diagonal reproduces H
+  return h + notdiag * 0x8000u;
 }
 
 // ---- register band fill + walk: one thread = one PAIR of tasks ---------------------------------
-// hstore: one contiguous block per warp, packed H of band cell (n, b) of lane l at block[(n*BW + b) * 32 + l]: a warp's
+// hstore: one contiguous block per warp, packed value of band cell (n, b) of lane l at block[(n*BW + b) * 32 + l]: a warp's
 //         store is one 128-byte line, consecutive cells are adjacent (streaming writes, TLB-friendly walk reads)
 // selectors: shared memory, sel[k * THREADS + tid], k = n + b
 template <int BW, bool HAS_N, int THREADS>
@@ -325,35 +390,29 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
     const int nrows = max(ga.rows, gb.rows);
     if (nrows > max_rows) { atomicOr(a.err_flag, 2u); continue; }
 
-    for (int k = 0; k < nrows + BW - 1; ++k) sel[k * THREADS + tid] = (SelT)pair_selector<HAS_N>(va, vb, ga.c0 + k, gb.c0 + k);
+    build_selectors<HAS_N>(va, vb, ga.c0, gb.c0, nrows + BW - 1, [&](int k, uint32_t v) { sel[k * THREADS + tid] = (SelT)v; });
 
     uint32_t Hd[BW], Fv[BW];
 #pragma unroll
     for (int b = 0; b < BW; ++b) { Hd[b] = NEG_OE; Fv[b] = NEG_OE; }
+    RowCodes ra, rb; ra.init(&va, ga.i_first); rb.init(&vb, gb.i_first);
     for (int n = 0; n < nrows; ++n) {
-      const uint32_t pa = row_profile(va, ga.i_first + n, MM4, MX, N4);
-      const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
+      const uint32_t pa = ra.template profile<HAS_N>(n, MM4, MX, N4);
+      const uint32_t pb = rb.template profile<HAS_N>(n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
       const SelT* srow = sel + (size_t)n * THREADS + tid;
       uint32_t* hrow = hmine + (size_t)n * BW * 32;
 #pragma unroll
       for (int b = 0; b < BW; ++b) {
-        const uint32_t selv = srow[b * THREADS];
-        uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
-        if (HAS_N) { const uint32_t isn = prmt(selv, 0u, 0xBBAAu); sp = (sp & ~isn) | (POS_OE & isn); }
-        const uint32_t t = __vadd2(Hd[b], sp);                                  // H[i-1][j-1] + s
         const uint32_t up_hoe = (b + 1 < BW) ? Hd[b + 1] : NEG_OE, up_f = (b + 1 < BW) ? Fv[b + 1] : NEG_OE;
-        const uint32_t f = __viaddmax_s16x2(up_f, NEG_EXT, up_hoe);             // F[i][j]
-        e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);                              // E[i][j]
-        const uint32_t h = __vimax3_s16x2_relu(t, e, f);
-        const uint32_t hoe = __vadd2(h, NEG_OE);
-        hrow[b * 32] = h;
-        Hd[b] = hoe; Fv[b] = f; hoe_left = hoe;
+        uint32_t f;
+        hrow[b * 32] = band_cell<HAS_N>(pa, pb, srow[b * THREADS], Hd[b], up_hoe, up_f, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
+        Hd[b] = hoe_left; Fv[b] = f;
       }
     }
-    walk_h_and_emit(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> int { return (int)(hmine[(n * BW + b) * 32] & 0xFFFFu); });
+    walk_h_and_emit<HAS_N>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
     if (haveB)
-      walk_h_and_emit(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> int { return (int)(hmine[(n * BW + b) * 32] >> 16); });
+      walk_h_and_emit<HAS_N>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
   }
 }
 
@@ -390,34 +449,28 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
     const int nrows = max(ga.rows, gb.rows);
     if (nrows > max_rows || bw > bw_cap) { atomicOr(a.err_flag, 2u); continue; }
 
-    for (int k = 0; k < nrows + bw - 1; ++k) sel[k * THREADS + tid] = (SelT)pair_selector<HAS_N>(va, vb, ga.c0 + k, gb.c0 + k);
+    build_selectors<HAS_N>(va, vb, ga.c0, gb.c0, nrows + bw - 1, [&](int k, uint32_t v) { sel[k * THREADS + tid] = (SelT)v; });
     for (int b = 0; b < bw; ++b) { Hd[b * THREADS + tid] = NEG_OE; Fv[b * THREADS + tid] = NEG_OE; }
 
+    RowCodes ra, rb; ra.init(&va, ga.i_first); rb.init(&vb, gb.i_first);
     for (int n = 0; n < nrows; ++n) {
-      const uint32_t pa = row_profile(va, ga.i_first + n, MM4, MX, N4);
-      const uint32_t pb = row_profile(vb, gb.i_first + n, MM4, MX, N4);
+      const uint32_t pa = ra.template profile<HAS_N>(n, MM4, MX, N4);
+      const uint32_t pb = rb.template profile<HAS_N>(n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
       uint32_t diag = Hd[tid];                                // old Hd[0]
       uint32_t* hrow = hmine + (size_t)n * bw * 32;
       for (int b = 0; b < bw; ++b) {
-        const uint32_t selv = sel[(n + b) * THREADS + tid];
-        uint32_t sp = prmt(pa, pb, selv & 0xFFFFu);
-        if (HAS_N) { const uint32_t isn = prmt(selv, 0u, 0xBBAAu); sp = (sp & ~isn) | (POS_OE & isn); }
-        const uint32_t t = __vadd2(diag, sp);
         uint32_t up_hoe = NEG_OE, up_f = NEG_OE;
         if (b + 1 < bw) { up_hoe = Hd[(b + 1) * THREADS + tid]; up_f = Fv[(b + 1) * THREADS + tid]; }
-        const uint32_t f = __viaddmax_s16x2(up_f, NEG_EXT, up_hoe);
-        e = __viaddmax_s16x2(e, NEG_EXT, hoe_left);
-        const uint32_t h = __vimax3_s16x2_relu(t, e, f);
-        const uint32_t hoe = __vadd2(h, NEG_OE);
-        hrow[b * 32] = h;
-        Hd[b * THREADS + tid] = hoe; Fv[b * THREADS + tid] = f; hoe_left = hoe;
+        uint32_t f;
+        hrow[b * 32] = band_cell<HAS_N>(pa, pb, sel[(n + b) * THREADS + tid], diag, up_hoe, up_f, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
+        Hd[b * THREADS + tid] = hoe_left; Fv[b * THREADS + tid] = f;
         diag = up_hoe;
       }
     }
-    walk_h_and_emit(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * 32] & 0xFFFFu); });
+    walk_h_and_emit<HAS_N>(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> uint32_t { return hmine[((size_t)n * bw + b) * 32] & 0xFFFFu; });
     if (haveB)
-      walk_h_and_emit(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> int { return (int)(hmine[((size_t)n * bw + b) * 32] >> 16); });
+      walk_h_and_emit<HAS_N>(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> uint32_t { return hmine[((size_t)n * bw + b) * 32] >> 16; });
   }
 }
 

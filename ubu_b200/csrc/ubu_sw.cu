@@ -351,7 +351,8 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
   CU(h, cudaEventRecord(s.ev_fork, st));
   for (int k = 0; k < 3; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
-  tb_diag_kernel<<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
+  if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
+  else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
   CU(h, cudaGetLastError()); ++s.n_launches;
   {
     const int grid = h->sm_count * TB_GRID_PER_SM;
