@@ -47,7 +47,7 @@ namespace ubu {
 template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
 __global__ void __launch_bounds__(THREADS, UBU_FWD_MIN_BLOCKS)
 sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
-                const uint32_t* __restrict__ order, uint32_t n_slots, Scoring sc,
+                const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks, Scoring sc,
                 FwdOut* __restrict__ out, int sel_stride) {
   static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide the warp");
   constexpr int GP = THREADS / G;
@@ -62,8 +62,9 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
 
   // ---- the pair of tasks of this group --------------------------------------------------
   const uint32_t slotA = 2u * (blockIdx.x * GP + grp), slotB = slotA + 1u;
-  const uint32_t tA = slotA < n_slots ? order[slotA] : 0xFFFFFFFFu;
-  const uint32_t tB = slotB < n_slots ? order[slotB] : 0xFFFFFFFFu;
+  uint32_t tA = 0xFFFFFFFFu, tB = 0xFFFFFFFFu;
+  if (order) { if (slotA < n_slots) tA = order[slotA]; if (slotB < n_slots) tB = order[slotB]; }
+  else { if (slotA < n_tasks) tA = slotA; if (slotB < n_tasks) tB = slotB; }
   int LA = 0, WA = 0, LB = 0, WB = 0;
   const uint8_t *qA = nullptr, *qB = nullptr, *rA = nullptr, *rB = nullptr;
   const uint8_t *qnA = nullptr, *qnB = nullptr, *rnA = nullptr, *rnB = nullptr;

@@ -65,12 +65,13 @@ __host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdO
 }
 
 // ---- classify ------------------------------------------------------------------------------
-__global__ void tb_plan_kernel(const uint32_t* __restrict__ order, uint32_t n_slots, const FwdOut* __restrict__ fwd,
+__global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks,
+                               const FwdOut* __restrict__ fwd,
                                Scoring sc, int smem_bw_cap, ubu_sw_result* __restrict__ res,
                                uint32_t* __restrict__ lists /* [TB_CLASSES][n_slots] */, unsigned int* __restrict__ counts) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1; uint32_t task = 0xFFFFFFFFu;
-  if (idx < n_slots) task = order[idx];
+  if (order) { if (idx < n_slots) task = order[idx]; } else if (idx < n_tasks) task = idx;
   if (task != 0xFFFFFFFFu) {
     const FwdOut f = fwd[task];
     if (f.score <= 0) {

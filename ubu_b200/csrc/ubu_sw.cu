@@ -62,7 +62,7 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; };
+struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; };
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -87,6 +87,7 @@ struct Slot {
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
   bool any_n = false, have_idx = false, reads_n = false, wins_n = false;
+  bool identity_order = false;           // uniform batch: tasks run in input order, no order array at all
   int lmax = 0, bw_cap = 0, smem_bw_cap = 0;
   unsigned int cig_cap = 0;
   int n_launches = 0;
@@ -139,7 +140,7 @@ cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs
   }
   const uint32_t pairs = L.n_slots / 2;
   const uint32_t grid = (pairs + GP - 1) / GP;
-  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, order + L.begin, L.n_slots, sc, out, stride);
+  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, order ? order + L.begin : nullptr, L.n_slots, L.n_tasks, sc, out, stride);
   return cudaGetLastError();
 }
 
@@ -174,6 +175,41 @@ int validate_seqs(const ubu_sw_seqs* s) {
 // ---- plan: class per task, order by (class, window length), pad classes to pairs ------------------
 int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx) {
   const uint32_t n = reads->count;
+  s.identity_order = false;
+  // ---- uniform batch (one read-length class, one window length, no N in any window): the common shape of a
+  //      realignment batch. Only bounds are checked (vectorisable passes); tasks keep their input order.
+  {
+    uint16_t lmin = 0xFFFF, lmax = 0, wmin = 0xFFFF, wmax = 0;
+    for (uint32_t t = 0; t < n; ++t) { const uint16_t L = reads->len[t]; lmin = std::min(lmin, L); lmax = std::max(lmax, L); }
+    for (uint32_t w = 0; w < wins->count; ++w) { const uint16_t W = wins->len[w]; wmin = std::min(wmin, W); wmax = std::max(wmax, W); }
+    bool win_n = false;
+    if (wins->nmask) {
+      if (wins->count && (uint64_t)wins->nmask_off[wins->count - 1] + ((uint32_t)wins->len[wins->count - 1] + 7u) / 8u > wins->nmask_bytes) return UBU_SW_ERR_ARG;
+      // any N at all in the window planes? (bytes between sequences are zero in every packer of this repo; a stray bit only costs speed)
+      const uint8_t* m = wins->nmask; uint8_t any = 0;
+      for (uint32_t k = 0; k < wins->nmask_bytes; ++k) any |= m[k];
+      win_n = any != 0;
+    }
+    const int c0 = cfg_of_len(lmin), c1 = cfg_of_len(lmax);
+    if (n && wins->count && c1 < 0) return UBU_SW_ERR_TOO_LONG;
+    if (n && wins->count && c0 == c1 && wmin == wmax && !win_n) {
+      uint32_t bad = 0, imax = 0;
+      const uint32_t rbytes = ((uint32_t)lmax + 3u) / 4u, wbytes = ((uint32_t)wmax + 3u) / 4u;
+      for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->off[t] + rbytes > reads->packed_bytes);
+      for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->off[w] + wbytes > wins->packed_bytes);
+      if (idx) { for (uint32_t t = 0; t < n; ++t) imax = std::max(imax, idx[t]); if (imax >= wins->count) bad = 1; }
+      if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)lmax + 7u) / 8u > reads->nmask_bytes);
+      if (wins->nmask) for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->nmask_off[w] + ((uint32_t)wmax + 7u) / 8u > wins->nmask_bytes);
+      if (bad) return UBU_SW_ERR_ARG;
+      if (fwd_smem_bytes(c1, false, wmax) > kMaxDynSmem) return UBU_SW_ERR_TOO_LONG;
+      s.lmax = lmax;
+      s.n_slots = (n + 1u) & ~1u;
+      s.identity_order = true;
+      s.launches.clear();
+      s.launches.push_back(FwdLaunch{c1, false, 0u, s.n_slots, (int)wmax, n});
+      return UBU_SW_OK;
+    }
+  }
   std::vector<uint8_t> win_has_n;
   if (wins->nmask) {
     win_has_n.assign(wins->count, 0);
@@ -248,7 +284,7 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       }
       int wm = 0;
       for (uint32_t k = beg; k < end && k < cnt[b]; ++k) wm = std::max(wm, (int)(s.tmp_keys[lo[k]] & 0xFFFFu));
-      s.launches.push_back(FwdLaunch{cfg, has_n, start[b] + beg, end - beg, wm});
+      s.launches.push_back(FwdLaunch{cfg, has_n, start[b] + beg, end - beg, wm, 0u});
       beg = end;
     }
   }
@@ -320,7 +356,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     CU(h, cudaMemcpyAsync(s.d_wnoff.p, wins->nmask_off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
   }
   if (idx) CU(h, cudaMemcpyAsync(s.d_idx.p, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(s.d_order.p, s.h_order.p, sizeof(uint32_t) * s.n_slots, cudaMemcpyHostToDevice, st));
+  if (!s.identity_order) CU(h, cudaMemcpyAsync(s.d_order.p, s.h_order.p, sizeof(uint32_t) * s.n_slots, cudaMemcpyHostToDevice, st));
   s.staged = true;
   return UBU_SW_OK;
 }
@@ -335,8 +371,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   DevSeqs reads{s.d_rp.p, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
   DevSeqs wins{s.d_wp.p, s.d_woff.p, s.d_wlen.p, s.wins_n ? s.d_wn.p : nullptr, s.wins_n ? s.d_wnoff.p : nullptr};
   const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
+  const uint32_t* d_order = s.identity_order ? nullptr : s.d_order.p;
   for (const FwdLaunch& L : s.launches) {
-    CU(h, launch_fwd(L, reads, wins, idx, s.d_order.p, h->sc, s.d_fwd.p, st));
+    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, st));
     ++s.n_launches;
   }
   CU(h, cudaEventRecord(s.ev[1], st));
@@ -345,7 +382,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
   a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 6; a.err_flag = s.d_ctr.p + 7;
   const int max_rows = std::max(s.lmax, 1);
-  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(s.d_order.p, s.n_slots, s.d_fwd.p, h->sc, s.smem_bw_cap, s.d_res.p, s.d_lists.p, s.d_ctr.p);
+  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(d_order, s.n_slots, s.n_tasks, s.d_fwd.p, h->sc, s.smem_bw_cap, s.d_res.p, s.d_lists.p, s.d_ctr.p);
   CU(h, cudaGetLastError()); ++s.n_launches;
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams

@@ -70,9 +70,20 @@ class SeqSet:
         return text_from_codes(self.codes(k))
 
     def slice(self, lo: int, hi: int) -> "SeqSet":
-        """Sequences [lo, hi) sharing the parent's packed buffers (offsets stay absolute)."""
-        return SeqSet(self.packed, self.off[lo:hi], self.len[lo:hi], self.nmask,
-                      None if self.nmask is None else self.nmask_off[lo:hi])
+        """Sequences [lo, hi) as a chunk of its own: zero-copy views of the packed bytes those sequences occupy, offsets
+        rebased to the view (so a submit() of the chunk uploads only the chunk). Assumes offsets ascend, as every packer
+        here produces them."""
+        if hi <= lo:
+            return SeqSet(self.packed[:0], self.off[:0], self.len[:0], None if self.nmask is None else self.nmask[:0],
+                          None if self.nmask is None else self.nmask_off[:0])
+        b0 = int(self.off[lo])
+        b1 = int(self.off[hi - 1]) + (int(self.len[hi - 1]) + 3) // 4
+        nmask = nmask_off = None
+        if self.nmask is not None:
+            m0 = int(self.nmask_off[lo])
+            m1 = int(self.nmask_off[hi - 1]) + (int(self.len[hi - 1]) + 7) // 8
+            nmask, nmask_off = self.nmask[m0:m1], (self.nmask_off[lo:hi] - np.uint32(m0)).astype(np.uint32)
+        return SeqSet(self.packed[b0:b1], (self.off[lo:hi] - np.uint32(b0)).astype(np.uint32), self.len[lo:hi], nmask, nmask_off)
 
 
 def pack_codes(code_arrays: Sequence[np.ndarray], force_nmask: bool = False) -> SeqSet:
