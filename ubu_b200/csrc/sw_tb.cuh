@@ -257,7 +257,33 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
     const TaskView t = load_task(a, task);
     const int S = f.score, je = f.je;
     int ie = 0, len = 0, edits = 0;
+    // Phase 1 (uniform across the warp): drop the candidate diagonals that cannot reach S, judged on their last 16
+    // columns only (popcount of differing bases; N counted as a match, so the bound stays an upper bound). Without it
+    // every lane of a warp pays for every other lane's full-length scan of ITS true diagonal.
+    uint32_t alive = 0u;
+    for (int i = f.i_lo; i <= f.i_hi; ++i) {
+      const int maxk = min(i, je);
+      bool keep = true;
+      if (maxk > 16 && S > 16 * ma) {
+        uint32_t x = load16(t.q, i - 16) ^ load16(t.r, je - 16);
+        x = (x | (x >> 1)) & 0x55555555u;
+        if (HAS_N) {
+          uint32_t nm = 0u;
+          if (t.qn) nm |= load16n(t.qn, i - 16);
+          if (t.rn) nm |= load16n(t.rn, je - 16);
+          uint32_t spread = 0u;                                 // bit u of nm -> bit 2u
+#pragma unroll
+          for (int u = 0; u < 16; ++u) spread |= ((nm >> u) & 1u) << (2 * u);
+          x &= ~spread;
+        }
+        const int d = __popc(x);
+        keep = (16 - d) * ma + d * mm + (maxk - 16) * ma >= S;
+      }
+      alive |= (keep ? 1u : 0u) << (i - f.i_lo);
+    }
+    // Phase 2: exact scan of the survivors in row order (usually exactly one).
     for (int i = f.i_lo; i <= f.i_hi && !ie; ++i) {
+      if (!((alive >> (i - f.i_lo)) & 1u)) continue;
       const int maxk = min(i, je);
       int run = 0, mism = 0;
       bool done = false;
