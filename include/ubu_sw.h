@@ -117,6 +117,45 @@ int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]);
 /* Number of kernel launches issued by the last run() on the slot. */
 int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot);
 
+/* ---- the steps right behind the aligner; bug-compatible with the Java they replace ---- */
+
+/* Long reference sequences (chromosomes), same 2-bit code + N plane; replaces the per-chromosome StringBuffer that
+ * CompareToReference.loadSeqRef rebuilds for every sequence (CompareToReference.java:125-149): uploaded once, kept in HBM. */
+typedef struct {
+  const uint8_t*  packed;
+  const uint64_t* off;          /* byte offset of sequence k in packed */
+  const uint32_t* len;          /* bases */
+  const uint8_t*  nmask;        /* optional */
+  const uint64_t* nmask_off;
+  uint32_t        count;
+  uint64_t        packed_bytes, nmask_bytes;
+} ubu_sw_refs;
+int ubu_sw_load_refs(ubu_sw_handle* h, const ubu_sw_refs* refs);
+
+#define UBU_SW_POST_NULL      1u   /* the reference returns a null read (ReAligner.java:1362-1364)                     */
+#define UBU_SW_POST_MALFORMED 2u   /* the reference throws (IllegalStateException / index out of bounds) or bad index  */
+#define UBU_SW_POST_POOL      4u   /* output CIGAR pool too small                                                      */
+
+/* An aligned read: reference sequence, 1-based POS, CIGAR slice (BAM ops, N = 3 allowed), MAPQ and the YQ / YM tags. */
+typedef struct { uint32_t ref_idx; int32_t pos; uint32_t cigar_off; uint16_t cigar_n; int16_t mapq; int16_t yq; int16_t ym; } ubu_sw_placed;
+typedef struct { int32_t xm, nm, mapq; uint32_t flags; } ubu_sw_recount;
+/* Replaces the per-read body of ReAligner.updateMismatchAndEditDistance (ReAligner.java:279-287): XM = numDifferences
+ * (CompareToReference.java:83-123), NM = XM + indel bases (:316-326), MAPQ = calcMappingQuality (:302-314).
+ * reads->count records; read k is described by placed[k]. Needs ubu_sw_load_refs first. */
+int ubu_sw_recount_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_placed* placed,
+                         const uint32_t* cigar_pool, size_t cigar_pool_n, ubu_sw_recount* out);
+
+/* A contig's own alignment to the genome (POS + CIGAR slice) and an ungapped placement of a read inside a contig. */
+typedef struct { int32_t pos; uint32_t cigar_off; uint32_t cigar_n; } ubu_sw_contig;
+typedef struct { uint32_t contig_idx; int32_t position /* 0-based offset in the contig (ReadPosition) */; uint32_t read_len; } ubu_sw_proj_in;
+typedef struct { int32_t pos; uint32_t cigar_off; uint16_t cigar_n; uint16_t flags; } ubu_sw_proj_out;
+/* Replaces ReAligner.updateReadAlignment (ReAligner.java:1293-1368) with ReadBlock's CIGAR algebra
+ * (ReadBlock.java:74-175): genome POS + CIGAR of each read, projected through its contig's CIGAR. */
+int ubu_sw_project_batch(ubu_sw_handle* h, const ubu_sw_contig* contigs, uint32_t n_contigs,
+                         const uint32_t* contig_cigar_pool, size_t contig_cigar_pool_n,
+                         const ubu_sw_proj_in* in, uint32_t n, ubu_sw_proj_out* out,
+                         uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);
+
 /* Pinned host memory for the caller's buffers (cudaHostAlloc); plain malloc'd buffers also work, slower. */
 void* ubu_sw_host_alloc(size_t bytes);
 void  ubu_sw_host_free(void* p);

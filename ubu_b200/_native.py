@@ -35,6 +35,15 @@ class Seqs(C.Structure):
     ]
 
 
+class Refs(C.Structure):
+    _fields_ = [
+        ("packed", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p), ("nmask", C.c_void_p), ("nmask_off", C.c_void_p),
+        ("count", C.c_uint32), ("packed_bytes", C.c_uint64), ("nmask_bytes", C.c_uint64),
+    ]
+
+
+POST_NULL, POST_MALFORMED, POST_POOL = 1, 2, 4
+
 # every symbol include/ubu_sw.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("ubu_sw_create", C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -48,6 +57,10 @@ SYMBOLS = [
     ("ubu_sw_fetch", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("ubu_sw_last_run_ms", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     ("ubu_sw_last_run_launches", C.c_int, [C.c_void_p, C.c_int]),
+    ("ubu_sw_load_refs", C.c_int, [C.c_void_p, C.POINTER(Refs)]),
+    ("ubu_sw_recount_batch", C.c_int, [C.c_void_p, C.POINTER(Seqs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("ubu_sw_project_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("ubu_sw_host_alloc", C.c_void_p, [C.c_size_t]),
     ("ubu_sw_host_free", None, [C.c_void_p]),
     ("ubu_sw_pack", None, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),

@@ -4,6 +4,7 @@
 // that needs the GPU fails with UBU_SW_ERR_NO_DEVICE / UBU_SW_ERR_CUDA when it is not there.
 #include "sw_fwd16.cuh"
 #include "sw_tb.cuh"
+#include "sw_post.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -103,6 +104,11 @@ struct ubu_sw_handle {
   Slot slots[4];
   std::string last_error;
   int next_slot = 0;
+  // resident reference sequences + scratch of the post-alignment calls (ubu_sw_load_refs / recount / project)
+  DevBuf<uint8_t> g_packed, g_nmask, p_bytes;
+  DevBuf<uint64_t> g_off, g_noff;
+  DevBuf<uint32_t> g_len, p_words;
+  uint32_t g_count = 0; bool g_has_n = false;
 };
 
 namespace {
@@ -548,6 +554,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
     s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release();
     s.h_order.release(); s.h_ctr.release();
+    if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     for (int e = 0; e < 3; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); }
@@ -633,6 +640,108 @@ int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_
   int rc = ubu_sw_submit(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, &ticket);
   if (rc) return rc;
   return ubu_sw_wait(h, ticket, cigar_pool_used);
+}
+
+int ubu_sw_load_refs(ubu_sw_handle* h, const ubu_sw_refs* r) {
+  if (!h || !r || (r->count && (!r->packed || !r->off || !r->len)) || (r->nmask && !r->nmask_off)) return UBU_SW_ERR_ARG;
+  for (uint32_t k = 0; k < r->count; ++k) {
+    if (r->off[k] + ((uint64_t)r->len[k] + 3) / 4 > r->packed_bytes) return UBU_SW_ERR_ARG;
+    if (r->nmask && r->nmask_off[k] + ((uint64_t)r->len[k] + 7) / 8 > r->nmask_bytes) return UBU_SW_ERR_ARG;
+  }
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->slots[0].stream;
+  CU(h, h->g_packed.reserve(r->packed_bytes + 16)); CU(h, h->g_off.reserve(r->count)); CU(h, h->g_len.reserve(r->count));
+  CU(h, cudaMemcpyAsync(h->g_packed.p, r->packed, r->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->g_off.p, r->off, sizeof(uint64_t) * r->count, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->g_len.p, r->len, sizeof(uint32_t) * r->count, cudaMemcpyHostToDevice, st));
+  h->g_has_n = r->nmask != nullptr;
+  if (h->g_has_n) {
+    CU(h, h->g_nmask.reserve(r->nmask_bytes + 16)); CU(h, h->g_noff.reserve(r->count));
+    CU(h, cudaMemcpyAsync(h->g_nmask.p, r->nmask, r->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->g_noff.p, r->nmask_off, sizeof(uint64_t) * r->count, cudaMemcpyHostToDevice, st));
+  }
+  CU(h, cudaStreamSynchronize(st));
+  h->g_count = r->count;
+  return UBU_SW_OK;
+}
+
+int ubu_sw_recount_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_placed* placed, const uint32_t* cigar_pool,
+                         size_t cigar_pool_n, ubu_sw_recount* out) {
+  if (!h || !reads) return UBU_SW_ERR_ARG;
+  int rc = validate_seqs(reads); if (rc) return rc;
+  const uint32_t n = reads->count;
+  if (n == 0) return UBU_SW_OK;
+  if (!placed || !out || (cigar_pool_n && !cigar_pool)) return UBU_SW_ERR_ARG;
+  for (uint32_t t = 0; t < n; ++t) {
+    if ((uint64_t)reads->off[t] + ((uint32_t)reads->len[t] + 3u) / 4u > reads->packed_bytes) return UBU_SW_ERR_ARG;
+    if (reads->nmask && (uint64_t)reads->nmask_off[t] + ((uint32_t)reads->len[t] + 7u) / 8u > reads->nmask_bytes) return UBU_SW_ERR_ARG;
+    if ((uint64_t)placed[t].cigar_off + placed[t].cigar_n > cigar_pool_n) return UBU_SW_ERR_ARG;
+  }
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slots[0];
+  if (s.pending) return UBU_SW_ERR_BUSY;
+  cudaStream_t st = s.stream;
+  const bool rn = reads->nmask != nullptr;
+  CU(h, s.d_rp.reserve(reads->packed_bytes + 16)); CU(h, s.d_roff.reserve(n)); CU(h, s.d_rlen.reserve(n));
+  if (rn) { CU(h, s.d_rn.reserve(reads->nmask_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
+  const size_t b_placed = sizeof(ubu_sw_placed) * (size_t)n, b_out = sizeof(ubu_sw_recount) * (size_t)n;
+  CU(h, h->p_bytes.reserve(b_placed + b_out + 64)); CU(h, h->p_words.reserve(cigar_pool_n + 1));
+  ubu_sw_placed* d_placed = reinterpret_cast<ubu_sw_placed*>(h->p_bytes.p);
+  ubu_sw_recount* d_out = reinterpret_cast<ubu_sw_recount*>(h->p_bytes.p + ((b_placed + 15) & ~(size_t)15));
+  CU(h, cudaMemcpyAsync(s.d_rp.p, reads->packed, reads->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_roff.p, reads->off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_rlen.p, reads->len, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, st));
+  if (rn) {
+    CU(h, cudaMemcpyAsync(s.d_rn.p, reads->nmask, reads->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.d_rnoff.p, reads->nmask_off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  }
+  CU(h, cudaMemcpyAsync(d_placed, placed, b_placed, cudaMemcpyHostToDevice, st));
+  if (cigar_pool_n) CU(h, cudaMemcpyAsync(h->p_words.p, cigar_pool, sizeof(uint32_t) * cigar_pool_n, cudaMemcpyHostToDevice, st));
+  DevSeqs dr{s.d_rp.p, s.d_roff.p, s.d_rlen.p, rn ? s.d_rn.p : nullptr, rn ? s.d_rnoff.p : nullptr};
+  DevRefs dg{h->g_packed.p, h->g_off.p, h->g_len.p, h->g_has_n ? h->g_nmask.p : nullptr, h->g_has_n ? h->g_noff.p : nullptr};
+  post_recount_kernel<<<(n + 127) / 128, 128, 0, st>>>(dr, dg, h->g_count, d_placed, h->p_words.p, n, d_out);
+  CU(h, cudaGetLastError());
+  CU(h, cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return UBU_SW_OK;
+}
+
+int ubu_sw_project_batch(ubu_sw_handle* h, const ubu_sw_contig* contigs, uint32_t n_contigs, const uint32_t* contig_cigar_pool,
+                         size_t contig_cigar_pool_n, const ubu_sw_proj_in* in, uint32_t n, ubu_sw_proj_out* out,
+                         uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used) {
+  if (!h) return UBU_SW_ERR_ARG;
+  if (cigar_pool_used) *cigar_pool_used = 0;
+  if (n == 0) return UBU_SW_OK;
+  if (!in || !out || (n_contigs && !contigs) || (contig_cigar_pool_n && !contig_cigar_pool) || (cigar_pool_cap && !cigar_pool)) return UBU_SW_ERR_ARG;
+  for (uint32_t c = 0; c < n_contigs; ++c)
+    if ((uint64_t)contigs[c].cigar_off + contigs[c].cigar_n > contig_cigar_pool_n) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slots[0];
+  if (s.pending) return UBU_SW_ERR_BUSY;
+  cudaStream_t st = s.stream;
+  const size_t b_c = (sizeof(ubu_sw_contig) * (size_t)n_contigs + 15) & ~(size_t)15, b_in = (sizeof(ubu_sw_proj_in) * (size_t)n + 15) & ~(size_t)15,
+               b_out = (sizeof(ubu_sw_proj_out) * (size_t)n + 15) & ~(size_t)15;
+  CU(h, h->p_bytes.reserve(b_c + b_in + b_out + 64));
+  CU(h, h->p_words.reserve(contig_cigar_pool_n + cigar_pool_cap + 8));
+  ubu_sw_contig* d_c = reinterpret_cast<ubu_sw_contig*>(h->p_bytes.p);
+  ubu_sw_proj_in* d_in = reinterpret_cast<ubu_sw_proj_in*>(h->p_bytes.p + b_c);
+  ubu_sw_proj_out* d_out = reinterpret_cast<ubu_sw_proj_out*>(h->p_bytes.p + b_c + b_in);
+  uint32_t* d_ccig = h->p_words.p; uint32_t* d_pool = h->p_words.p + contig_cigar_pool_n;
+  CU(h, s.d_ctr.reserve(64));
+  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, sizeof(unsigned int), st));
+  if (n_contigs) CU(h, cudaMemcpyAsync(d_c, contigs, sizeof(ubu_sw_contig) * (size_t)n_contigs, cudaMemcpyHostToDevice, st));
+  if (contig_cigar_pool_n) CU(h, cudaMemcpyAsync(d_ccig, contig_cigar_pool, sizeof(uint32_t) * contig_cigar_pool_n, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(d_in, in, sizeof(ubu_sw_proj_in) * (size_t)n, cudaMemcpyHostToDevice, st));
+  post_project_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_c, n_contigs, d_ccig, d_in, n, d_out, d_pool, (unsigned)cigar_pool_cap, s.d_ctr.p);
+  CU(h, cudaGetLastError());
+  unsigned int used = 0;
+  CU(h, cudaMemcpyAsync(&used, s.d_ctr.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(out, d_out, sizeof(ubu_sw_proj_out) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  if (cigar_pool_used) *cigar_pool_used = used;
+  if (used > cigar_pool_cap) return UBU_SW_ERR_CIGAR_POOL;
+  if (used) CU(h, cudaMemcpy(cigar_pool, d_pool, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost));
+  return UBU_SW_OK;
 }
 
 void* ubu_sw_host_alloc(size_t bytes) {
