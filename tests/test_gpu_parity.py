@@ -107,3 +107,63 @@ def test_other_scoring(params):
     with U.SwAligner(*params) as a:
         al = a.align(w.reads, w.windows, w.pair_ref_idx)
     check_against_oracle(al, w.reads, w.windows, w.pair_ref_idx, params)
+
+
+def test_golden_vectors_through_the_c_abi():
+    """Every committed golden case (tests/golden/sw_golden_v1.json), grouped by scoring parameters."""
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sw_golden_v1.json")))
+    by_params = {}
+    for c in gold["cases"]:
+        by_params.setdefault(tuple(c["params"]), []).append(c)
+    for params, cases in by_params.items():
+        reads = U.pack_texts([c["read"] for c in cases], force_nmask=True)
+        wins = U.pack_texts([c["window"] for c in cases], force_nmask=True)
+        with U.SwAligner(*params) as a:
+            al = a.align(reads, wins)
+        for k, c in enumerate(cases):
+            e = c["expect"]
+            got = {f: int(al.results[k][f]) for f in FIELDS}
+            assert got == {f: e[f] for f in FIELDS}, (c["name"], got, e)
+            assert al.cigar_string(k) == e["cigar"], c["name"]
+            assert (int(al.results[k]["flags"]) & 1) == (e["flags"] & 1)
+
+
+def test_full_size_cfg2_properties(aligner):
+    """BASELINE.json configs[1] at full size (1M reads): properties that need no oracle, plus an oracle-checked sample."""
+    w = WL.cfg2(1_000_000, keep_codes=True)
+    al = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    r = al.results
+    n = len(al)
+    assert n == 1_000_000 and int((r["flags"] & 1).sum()) == 0
+    assert int(r["score"].max()) <= 76 and int(r["score"].min()) > 20
+    assert np.all(r["q_end"] >= r["q_start"]) and np.all(r["ref_end"] >= r["ref_start"]) and np.all(r["ref_end"] <= 500)
+    # CIGAR covers the read; reference span matches; every CIGAR slice lies inside the pool and slices do not overlap
+    ops = al.cigar_pool
+    lens, kinds = (ops >> 4).astype(np.int64), (ops & 15)
+    owner = np.repeat(np.arange(n), r["cigar_n"].astype(np.int64)[np.argsort(r["cigar_off"], kind="stable")])
+    order = np.argsort(r["cigar_off"], kind="stable")
+    assert int(r["cigar_n"].sum()) == ops.shape[0]
+    starts = r["cigar_off"][order].astype(np.int64)
+    assert np.array_equal(starts, np.concatenate([[0], np.cumsum(r["cigar_n"][order].astype(np.int64))[:-1]]))
+    qlen = np.zeros(n, dtype=np.int64); rlen = np.zeros(n, dtype=np.int64); gaps = np.zeros(n, dtype=np.int64)
+    task_of_op = order[owner]
+    np.add.at(qlen, task_of_op, np.where(np.isin(kinds, (0, 1, 4)), lens, 0))
+    np.add.at(rlen, task_of_op, np.where(np.isin(kinds, (0, 2)), lens, 0))
+    np.add.at(gaps, task_of_op, np.where(np.isin(kinds, (1, 2)), lens, 0))
+    assert np.all(qlen == 76)
+    assert np.all(rlen == r["ref_end"].astype(np.int64) - r["ref_start"] + 1)
+    assert np.all(r["edit_distance"] >= gaps)
+    # idempotence: a second run gives the same records
+    al2 = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    for f in FIELDS + ("cigar_n",):
+        assert np.array_equal(al2.results[f], r[f])
+    # oracle on a random sample of 5000 tasks
+    pick = np.sort(np.random.default_rng(1).choice(n, size=5000, replace=False))
+    q = [w.read_codes[k] for k in pick]
+    wi = [w.window_codes[int(w.pair_ref_idx[k])] for k in pick]
+    ores, ocig = O.align_batch(q, wi, None, nthreads=8)
+    for j, k in enumerate(pick):
+        assert all(int(r[int(k)][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(int(k)) == ocig[j]
