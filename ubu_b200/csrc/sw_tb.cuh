@@ -32,8 +32,9 @@ namespace ubu {
 
 constexpr int TB_NEG = -0x10000000;
 // band-width classes: 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 (registers),
-// 4: shared-memory band, 5: scalar last resort
-constexpr int TB_CLASSES = 6;
+// 4/5/6: shared-memory band <= cap[0] / cap[1] / cap[2] (narrower caps = more CTAs per SM), 7: scalar last resort
+constexpr int TB_CLASSES = 8;
+struct SmemCaps { int cap[3]; };
 
 struct TbArgs {
   DevSeqs reads, wins;
@@ -67,7 +68,7 @@ __host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdO
 // ---- classify ------------------------------------------------------------------------------
 __global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks,
                                const FwdOut* __restrict__ fwd,
-                               Scoring sc, int smem_bw_cap, ubu_sw_result* __restrict__ res,
+                               Scoring sc, SmemCaps caps, ubu_sw_result* __restrict__ res,
                                uint32_t* __restrict__ lists /* [TB_CLASSES][n_slots] */, unsigned int* __restrict__ counts) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1; uint32_t task = 0xFFFFFFFFu;
@@ -81,7 +82,7 @@ __global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = i
     } else {
       const int gb = gap_bound(sc, f.i_hi, f.score);
       const int bw = (f.i_hi - f.i_lo) + 2 * gb + 1;
-      cls = gb == 0 ? 0 : (bw <= 8 ? 1 : (bw <= 16 ? 2 : (bw <= 32 ? 3 : (bw <= smem_bw_cap ? 4 : 5))));
+      cls = gb == 0 ? 0 : (bw <= 8 ? 1 : (bw <= 16 ? 2 : (bw <= 32 ? 3 : (bw <= caps.cap[0] ? 4 : (bw <= caps.cap[1] ? 5 : (bw <= caps.cap[2] ? 6 : 7))))));
     }
   }
   const unsigned lane = threadIdx.x & 31u;
@@ -444,7 +445,7 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
 }
 
 // ---- shared-memory band fill + walk (any band width up to bw_cap) ---------------------------------
-// shared memory per CTA: Hd[bw_cap][THREADS] u32, Fv[bw_cap][THREADS] u32, sel[(max_rows + bw_cap)][THREADS] SelT
+// shared memory per CTA: HF[bw_cap][THREADS] uint2 (x = H - oe, y = F of the previous band row), sel[(max_rows + bw_cap)][THREADS] SelT
 // hstore: one block of max_rows*bw_cap cells per warp, cell (n, b) of lane l at block[(n * bw + b) * 32 + l] (bw = this pair's width)
 template <bool HAS_N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -452,9 +453,8 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
                     uint32_t* __restrict__ hstore, uint32_t* __restrict__ opscratch, int max_rows, int bw_cap) {
   using SelT = typename SelType<HAS_N>::type;
   extern __shared__ __align__(16) unsigned char tb_smem[];
-  uint32_t* Hd = reinterpret_cast<uint32_t*>(tb_smem);
-  uint32_t* Fv = Hd + (size_t)bw_cap * THREADS;
-  SelT* sel = reinterpret_cast<SelT*>(Fv + (size_t)bw_cap * THREADS);
+  uint2* HF = reinterpret_cast<uint2*>(tb_smem);
+  SelT* sel = reinterpret_cast<SelT*>(HF + (size_t)bw_cap * THREADS);
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x;
   const uint32_t n_tasks = *count, n_pairs = (n_tasks + 1u) / 2u;
@@ -477,22 +477,22 @@ tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned 
     if (nrows > max_rows || bw > bw_cap) { atomicOr(a.err_flag, 2u); continue; }
 
     build_selectors<HAS_N>(va, vb, ga.c0, gb.c0, nrows + bw - 1, [&](int k, uint32_t v) { sel[k * THREADS + tid] = (SelT)v; });
-    for (int b = 0; b < bw; ++b) { Hd[b * THREADS + tid] = NEG_OE; Fv[b * THREADS + tid] = NEG_OE; }
+    for (int b = 0; b < bw; ++b) HF[b * THREADS + tid] = make_uint2(NEG_OE, NEG_OE);
 
     RowCodes ra, rb; ra.init(&va, ga.i_first); rb.init(&vb, gb.i_first);
     for (int n = 0; n < nrows; ++n) {
       const uint32_t pa = ra.template profile<HAS_N>(n, MM4, MX, N4);
       const uint32_t pb = rb.template profile<HAS_N>(n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
-      uint32_t diag = Hd[tid];                                // old Hd[0]
+      uint32_t diag = HF[tid].x;                              // old H - oe of cell 0
       uint32_t* hrow = hmine + (size_t)n * bw * 32;
       for (int b = 0; b < bw; ++b) {
-        uint32_t up_hoe = NEG_OE, up_f = NEG_OE;
-        if (b + 1 < bw) { up_hoe = Hd[(b + 1) * THREADS + tid]; up_f = Fv[(b + 1) * THREADS + tid]; }
+        uint2 up = make_uint2(NEG_OE, NEG_OE);
+        if (b + 1 < bw) up = HF[(b + 1) * THREADS + tid];
         uint32_t f;
-        hrow[b * 32] = band_cell<HAS_N>(pa, pb, sel[(n + b) * THREADS + tid], diag, up_hoe, up_f, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
-        Hd[b * THREADS + tid] = hoe_left; Fv[b * THREADS + tid] = f;
-        diag = up_hoe;
+        hrow[b * 32] = band_cell<HAS_N>(pa, pb, sel[(n + b) * THREADS + tid], diag, up.x, up.y, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
+        HF[b * THREADS + tid] = make_uint2(hoe_left, f);
+        diag = up.x;
       }
     }
     walk_h_and_emit<HAS_N>(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> uint32_t { return hmine[((size_t)n * bw + b) * 32] & 0xFFFFu; });

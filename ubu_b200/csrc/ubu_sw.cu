@@ -29,7 +29,7 @@ constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
 constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
-constexpr int TBS_THREADS = 32, TBS_GRID_PER_SM = 2;     // shared-memory-band traceback
+constexpr int TBS_THREADS = 32;                          // shared-memory-band traceback (CTAs per SM depend on the band cap)
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
 constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
 
@@ -63,21 +63,25 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kAux = 5;
 struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; };
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};    // the traceback classes are independent: they run side by side
+  cudaStream_t aux[kAux] = {};                           // the traceback classes are independent: they run side by side
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
   DevBuf<uint8_t> d_rp, d_rn, d_wp, d_wn;
   DevBuf<uint32_t> d_roff, d_rnoff, d_woff, d_wnoff, d_idx, d_order, d_lists, d_cig;
   DevBuf<uint16_t> d_rlen, d_wlen;
   DevBuf<FwdOut> d_fwd;
   DevBuf<ubu_sw_result> d_res;
-  DevBuf<unsigned int> d_ctr;            // [0..5] class counts, [6] cigar cursor, [7] error flags
+  DevBuf<unsigned int> d_ctr;            // [0..7] class counts, [8] cigar cursor, [9] error flags
   DevBuf<uint32_t> d_hstore;             // packed H of every band cell: [BW=8 | BW=16 | BW=32 | shared-memory band] regions
-  size_t h_off[4] = {0, 0, 0, 0};
+  size_t h_off[6] = {0, 0, 0, 0, 0, 0};   // band 8 | 16 | 32 | shared-memory caps 0, 1, 2
+  size_t ops_off[3] = {0, 0, 0};
+  SmemCaps caps{{0, 0, 0}};
+  int tbs_ctas[3] = {0, 0, 0};           // CTAs per SM of the three shared-memory band classes
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
@@ -317,7 +321,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   if (idx) CU(h, s.d_idx.reserve(n));
   CU(h, s.d_order.reserve(s.n_slots)); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
   CU(h, s.d_fwd.reserve(n)); CU(h, s.d_res.reserve(n));
-  CU(h, s.d_ctr.reserve(8)); CU(h, s.h_ctr.reserve(8));
+  CU(h, s.d_ctr.reserve(64)); CU(h, s.h_ctr.reserve(16));
   if (s.cig_cap < 6u * n + 4096u) { s.cig_cap = 6u * n + 4096u; }
   CU(h, s.d_cig.reserve(s.cig_cap));
   // traceback scratch
@@ -325,21 +329,29 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   {
     const int gbmax = gap_bound(h->sc, max_rows, 1);
     s.bw_cap = std::min(kMaxK + 2 * gbmax + 1, max_rows + 65535);
-    // widest band whose rows (Hd, Fv: 2 x u32) and selectors fit the shared-memory kernel
+    // widest band whose rows (H - oe, F: 2 x u32 per cell) and selectors fit the shared-memory kernel
     const size_t selsz = s.any_n ? 4 : 2;
     const long avail = (long)kMaxDynSmem - (long)max_rows * TBS_THREADS * (long)selsz;
     long cap = avail > 0 ? avail / (long)(TBS_THREADS * (8 + selsz)) : 0;
     s.smem_bw_cap = (int)std::max<long>(0, std::min<long>(cap, s.bw_cap));
+    s.caps.cap[0] = std::min(64, s.smem_bw_cap); s.caps.cap[1] = std::min(128, s.smem_bw_cap); s.caps.cap[2] = s.smem_bw_cap;
     const size_t reg_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
-    const size_t smem_threads = (size_t)h->sm_count * TBS_GRID_PER_SM * TBS_THREADS;
     s.h_off[0] = 0;
     s.h_off[1] = s.h_off[0] + reg_threads * (size_t)max_rows * 8;
     s.h_off[2] = s.h_off[1] + reg_threads * (size_t)max_rows * 16;
     s.h_off[3] = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
-    size_t hwords = s.h_off[3];
-    if (s.smem_bw_cap > 32) hwords += smem_threads * (size_t)max_rows * (size_t)s.smem_bw_cap;
+    size_t hwords = s.h_off[3], opwords = 0;
+    for (int c = 0; c < 3; ++c) {
+      const int bc = s.caps.cap[c];
+      const size_t smem = (size_t)bc * TBS_THREADS * 8 + (size_t)(max_rows + bc) * TBS_THREADS * selsz;
+      s.tbs_ctas[c] = (bc > 32 && (c == 0 || bc > s.caps.cap[c - 1])) ? (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 0;
+      const size_t threads = (size_t)h->sm_count * s.tbs_ctas[c] * TBS_THREADS;
+      s.h_off[3 + c] = hwords; s.ops_off[c] = opwords;
+      hwords += threads * (size_t)max_rows * (size_t)bc;
+      opwords += threads * (size_t)(2 * bc + max_rows + 8);
+    }
     CU(h, s.d_hstore.reserve(hwords));
-    CU(h, s.d_ops.reserve(smem_threads * (size_t)(2 * s.smem_bw_cap + max_rows + 8)));
+    CU(h, s.d_ops.reserve(opwords + 8));
     if (s.bw_cap > s.smem_bw_cap) {
       const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
       CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
@@ -373,7 +385,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   s.n_launches = 0;
   CU(h, cudaEventRecord(s.ev[0], st));
   if (s.n_tasks == 0) { CU(h, cudaEventRecord(s.ev[1], st)); CU(h, cudaEventRecord(s.ev[2], st)); s.ran = true; return UBU_SW_OK; }
-  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, 8 * sizeof(unsigned int), st));
+  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, 16 * sizeof(unsigned int), st));
   DevSeqs reads{s.d_rp.p, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
   DevSeqs wins{s.d_wp.p, s.d_woff.p, s.d_wlen.p, s.wins_n ? s.d_wn.p : nullptr, s.wins_n ? s.d_wnoff.p : nullptr};
   const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
@@ -386,14 +398,14 @@ int do_run(ubu_sw_handle* h, Slot& s) {
 
   TbArgs a;
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
-  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 6; a.err_flag = s.d_ctr.p + 7;
+  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 8; a.err_flag = s.d_ctr.p + 9;
   const int max_rows = std::max(s.lmax, 1);
-  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(d_order, s.n_slots, s.n_tasks, s.d_fwd.p, h->sc, s.smem_bw_cap, s.d_res.p, s.d_lists.p, s.d_ctr.p);
+  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(d_order, s.n_slots, s.n_tasks, s.d_fwd.p, h->sc, s.caps, s.d_res.p, s.d_lists.p, s.d_ctr.p);
   CU(h, cudaGetLastError()); ++s.n_launches;
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
   CU(h, cudaEventRecord(s.ev_fork, st));
-  for (int k = 0; k < 3; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
+  for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
   if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
   else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
   CU(h, cudaGetLastError()); ++s.n_launches;
@@ -426,28 +438,31 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     }
     s.n_launches += 3;
   }
-  if (s.smem_bw_cap > 32) {
+  for (int c = 0; c < 3; ++c) {                       // shared-memory bands: narrow caps first, each on its own stream
+    if (!s.tbs_ctas[c]) continue;
+    const int bc = s.caps.cap[c];
     const size_t selsz = s.any_n ? 4 : 2;
-    const size_t smem = (size_t)s.smem_bw_cap * TBS_THREADS * 8 + (size_t)(max_rows + s.smem_bw_cap) * TBS_THREADS * selsz;
-    const int grid = h->sm_count * TBS_GRID_PER_SM;
-    uint32_t* hs = s.d_hstore.p + s.h_off[3];
+    const size_t smem = (size_t)bc * TBS_THREADS * 8 + (size_t)(max_rows + bc) * TBS_THREADS * selsz;
+    const int grid = h->sm_count * s.tbs_ctas[c];
+    uint32_t* hs = s.d_hstore.p + s.h_off[3 + c];
+    uint32_t* ops = s.d_ops.p + s.ops_off[c];
     if (s.any_n) {
       auto k = tb_fill_smem_kernel<true, TBS_THREADS>;
       if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, s.aux[2]>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, hs, s.d_ops.p, max_rows, s.smem_bw_cap);
+      k<<<grid, TBS_THREADS, smem, s.aux[2 + c]>>>(a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c, hs, ops, max_rows, bc);
     } else {
       auto k = tb_fill_smem_kernel<false, TBS_THREADS>;
       if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, s.aux[2]>>>(a, s.d_lists.p + 4 * NS, s.d_ctr.p + 4, hs, s.d_ops.p, max_rows, s.smem_bw_cap);
+      k<<<grid, TBS_THREADS, smem, s.aux[2 + c]>>>(a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c, hs, ops, max_rows, bc);
     }
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
   if (s.bw_cap > s.smem_bw_cap) {
-    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[2]>>>(a, s.d_lists.p + 5 * NS, s.d_ctr.p + 5,
+    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
                                                                               s.d_wide.p, max_rows, s.bw_cap);
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
-  for (int k = 0; k < 3; ++k) {                       // join
+  for (int k = 0; k < kAux; ++k) {                    // join
     CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
     CU(h, cudaStreamWaitEvent(st, s.ev_join[k], 0));
   }
@@ -463,9 +478,9 @@ int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size
   if (!out) return UBU_SW_ERR_ARG;
   cudaStream_t st = s.stream;
   for (int attempt = 0;; ++attempt) {
-    CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
-    const unsigned int need = s.h_ctr.p[6], err = s.h_ctr.p[7];
+    const unsigned int need = s.h_ctr.p[8], err = s.h_ctr.p[9];
     if (err & 2u) { h->last_error = "internal: traceback left its band (please report)"; return UBU_SW_ERR_CUDA; }
     if (err & 1u) {                    // device CIGAR pool was too small: grow it and redo the device work once
       if (attempt) { h->last_error = "internal: CIGAR pool overflow after regrow"; return UBU_SW_ERR_CUDA; }
@@ -534,7 +549,7 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
     for (int e = 0; e < 3; ++e)
       if (cudaEventCreate(&h->slots[i].ev[e]) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&h->slots[i].ev_fork, cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
-    for (int e = 0; e < 3; ++e) {
+    for (int e = 0; e < kAux; ++e) {
       if (cudaStreamCreateWithFlags(&h->slots[i].aux[e], cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
       if (cudaEventCreateWithFlags(&h->slots[i].ev_join[e], cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     }
@@ -557,7 +572,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-    for (int e = 0; e < 3; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); }
+    for (int e = 0; e < kAux; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   delete h;
