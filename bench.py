@@ -338,7 +338,9 @@ def main():
                            f"4 ALU : 3 VIADD cell mix at {peak['sm_mhz']:.0f} MHz x 148 SMs x 32 lanes x 2 cells / 7 ops",
             "alu_pipe_only_peak": peak.get("alu_only_roofline_gcups"),
             "ops_per_cell": 7, "launch_ms": fwd_s * 1e3, "share_of_step": float(np.mean(fwd_ms) / np.mean(ev_ms)),
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu capture
+            # (profiles/fwd16_r01.txt: 94.57 MB + 6.65 MB); only meaningful for the default 1M-read cfg2 launch
+            "traffic": 101.2e6 if n == 1_000_000 else None, "traffic_unit": "bytes per launch (ncu, profiles/fwd16_r01.txt)",
             "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": 6551.4,
                     "frac": algo_bytes / fwd_s / 1e9 / 6551.4, "note": "not the bound: ~2e-3 B/cell"},
         }
