@@ -21,10 +21,10 @@
 // A comparison that holds in the full matrix involves a cell of the SPEC path (exact in the band);
 // one that fails in the full matrix fails a fortiori with banded values (they are lower bounds).
 //
-// Kernels: tb_plan_kernel sorts tasks into band-width classes; tb_fill_reg_kernel<BW> keeps the
-// band row in registers (BW = 16 or 32 diagonals); tb_fill_smem_kernel keeps it in shared memory
-// (any width that fits); tb_wide_kernel (scalar, global scratch, direction bits) is the last resort
-// for bands too wide for shared memory (extreme scoring parameters only).
+// Kernels: tb_plan_kernel sorts tasks into band-width classes; tb_diag_kernel handles the gap-free class;
+// tb_fill_reg_kernel<BW> keeps the band row in registers (BW = 8, 16 or 32 diagonals); wider bands go to
+// tb_rect_kernel (sw_tbrect.cuh); tb_wide_kernel (scalar, global scratch, direction bits) is the last
+// resort (extreme scoring parameters / very long windows only).
 #pragma once
 #include "sw_common.cuh"
 
@@ -32,9 +32,9 @@ namespace ubu {
 
 constexpr int TB_NEG = -0x10000000;
 // band-width classes: 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 (registers),
-// 4/5/6: shared-memory band <= cap[0] / cap[1] / cap[2] (narrower caps = more CTAs per SM), 7: scalar last resort
+// 4/5/6: wide bands, systolic rectangle fill (sw_tbrect.cuh) with rows <= rows[c] and width <= wcap[c], 7: scalar last resort
 constexpr int TB_CLASSES = 8;
-struct SmemCaps { int cap[3]; };
+struct RectCaps { int rows[3]; int wcap[3]; };
 
 struct TbArgs {
   DevSeqs reads, wins;
@@ -68,7 +68,7 @@ __host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdO
 // ---- classify ------------------------------------------------------------------------------
 __global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks,
                                const FwdOut* __restrict__ fwd,
-                               Scoring sc, SmemCaps caps, ubu_sw_result* __restrict__ res,
+                               Scoring sc, RectCaps caps, ubu_sw_result* __restrict__ res,
                                uint32_t* __restrict__ lists /* [TB_CLASSES][n_slots] */, unsigned int* __restrict__ counts) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1; uint32_t task = 0xFFFFFFFFu;
@@ -82,7 +82,16 @@ __global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = i
     } else {
       const int gb = gap_bound(sc, f.i_hi, f.score);
       const int bw = (f.i_hi - f.i_lo) + 2 * gb + 1;
-      cls = gb == 0 ? 0 : (bw <= 8 ? 1 : (bw <= 16 ? 2 : (bw <= 32 ? 3 : (bw <= caps.cap[0] ? 4 : (bw <= caps.cap[1] ? 5 : (bw <= caps.cap[2] ? 6 : 7))))));
+      if (gb == 0) cls = 0;
+      else if (bw <= 8) cls = 1;
+      else if (bw <= 16) cls = 2;
+      else if (bw <= 32) cls = 3;
+      else {
+        const int clo = max(1, 1 + f.je - f.i_hi - gb), w = f.je - clo + 1;       // rectangle of sw_tbrect.cuh
+        cls = 7;
+#pragma unroll
+        for (int c = 2; c >= 0; --c) if (f.i_hi <= caps.rows[c] && w <= caps.wcap[c]) cls = 4 + c;
+      }
     }
   }
   const unsigned lane = threadIdx.x & 31u;
@@ -140,7 +149,8 @@ __device__ __forceinline__ void emit_result(const TbArgs& a, uint32_t task, cons
 // Walk on the stored band values (see the header comment). WordAt(n, b) returns the 16-bit value of band cell b in
 // band row n (n = i - i_first) for THIS task's half: bits 0-14 = H, bit 15 = diagonal does not reproduce H.
 // Rows above i_first are the zero boundary; cells left of column 1 were filled as H = 0.
-template <bool HAS_N, class WordAt>
+// USE_FLAG = false: the store holds H only and the diagonal test is made from the sequences (16 bases per load).
+template <bool HAS_N, bool USE_FLAG, class WordAt>
 __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, const TaskView& t, const Band& g, int bw,
                                                 uint32_t* opbuf, WordAt word_at) {
   const int ma = a.sc.match, mm = a.sc.mismatch, open = a.sc.gap_open, ext = a.sc.gap_ext;
@@ -167,11 +177,24 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
     uint32_t w[WB + 1];
 #pragma unroll
     for (int k = 0; k <= WB; ++k) w[k] = (n - k >= 0) ? word_at(n - k, b) : 0u;
+    uint32_t xdiff = 0u, xn = 0u;                          // !USE_FLAG: base (i-1-k) vs (j-1-k) differ / involve N, at bit 2*(15-k) / (15-k)
+    if (!USE_FLAG) {
+      xdiff = load16(t.q, i - 16) ^ load16(t.r, j - 16);
+      xdiff = (xdiff | (xdiff >> 1)) & 0x55555555u;
+      if (HAS_N) { if (t.qn) xn |= load16n(t.qn, i - 16); if (t.rn) xn |= load16n(t.rn, j - 16); }
+    }
     bool stop = false;
 #pragma unroll
     for (int k = 0; k < WB; ++k) {
       if (!stop) {
-        if (h > 0 && !(w[k] & 0x8000u)) { o.push(UBU_SW_CIGAR_M, 1u); ++n_m; --i; --j; h = (int)(w[k + 1] & 0x7FFFu); }
+        bool diag;
+        if (USE_FLAG) diag = !(w[k] & 0x8000u);
+        else {
+          const bool isn = HAS_N && ((xn >> (15 - k)) & 1u);
+          const int sk = isn ? 0 : (((xdiff >> (2 * (15 - k))) & 1u) ? mm : ma);
+          diag = (i >= 1 && j >= 1) && ((int)(w[k + 1] & 0x7FFFu) + sk == h);
+        }
+        if (h > 0 && diag) { o.push(UBU_SW_CIGAR_M, 1u); ++n_m; --i; --j; h = (int)(w[k + 1] & 0x7FFFu); }
         else stop = true;
       }
     }
@@ -438,66 +461,9 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
         Hd[b] = hoe_left; Fv[b] = f;
       }
     }
-    walk_h_and_emit<HAS_N>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
+    walk_h_and_emit<HAS_N, true>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
     if (haveB)
-      walk_h_and_emit<HAS_N>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
-  }
-}
-
-// ---- shared-memory band fill + walk (any band width up to bw_cap) ---------------------------------
-// shared memory per CTA: HF[bw_cap][THREADS] uint2 (x = H - oe, y = F of the previous band row), sel[(max_rows + bw_cap)][THREADS] SelT
-// hstore: one block of max_rows*bw_cap cells per warp, cell (n, b) of lane l at block[(n * bw + b) * 32 + l] (bw = this pair's width)
-template <bool HAS_N, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-tb_fill_smem_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
-                    uint32_t* __restrict__ hstore, uint32_t* __restrict__ opscratch, int max_rows, int bw_cap) {
-  using SelT = typename SelType<HAS_N>::type;
-  extern __shared__ __align__(16) unsigned char tb_smem[];
-  uint2* HF = reinterpret_cast<uint2*>(tb_smem);
-  SelT* sel = reinterpret_cast<SelT*>(HF + (size_t)bw_cap * THREADS);
-  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int tid = threadIdx.x;
-  const uint32_t n_tasks = *count, n_pairs = (n_tasks + 1u) / 2u;
-  const int oe = a.sc.gap_open + a.sc.gap_ext;
-  const uint32_t mmb = (uint32_t)(a.sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(a.sc.match + oe) & 0xFFu;
-  const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
-  const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
-  uint32_t* hmine = hstore + (size_t)(gtid >> 5) * ((size_t)max_rows * bw_cap * 32) + (gtid & 31u);
-  uint32_t* opbuf = opscratch + (size_t)gtid * (size_t)(2 * bw_cap + max_rows + 8);
-
-  for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
-    const uint32_t tA = list[2u * pair];
-    const bool haveB = 2u * pair + 1u < n_tasks;
-    const uint32_t tB = haveB ? list[2u * pair + 1u] : tA;
-    const TaskView va = load_task(a, tA), vb = load_task(a, tB);
-    const Band na = make_band(a.sc, a.fwd[tA], 0), nb = make_band(a.sc, a.fwd[tB], 0);
-    const int bw = max(na.bw, nb.bw);                         // both halves sweep the wider band
-    const Band ga = make_band(a.sc, a.fwd[tA], bw), gb = make_band(a.sc, a.fwd[tB], bw);
-    const int nrows = max(ga.rows, gb.rows);
-    if (nrows > max_rows || bw > bw_cap) { atomicOr(a.err_flag, 2u); continue; }
-
-    build_selectors<HAS_N>(va, vb, ga.c0, gb.c0, nrows + bw - 1, [&](int k, uint32_t v) { sel[k * THREADS + tid] = (SelT)v; });
-    for (int b = 0; b < bw; ++b) HF[b * THREADS + tid] = make_uint2(NEG_OE, NEG_OE);
-
-    RowCodes ra, rb; ra.init(&va, ga.i_first); rb.init(&vb, gb.i_first);
-    for (int n = 0; n < nrows; ++n) {
-      const uint32_t pa = ra.template profile<HAS_N>(n, MM4, MX, N4);
-      const uint32_t pb = rb.template profile<HAS_N>(n, MM4, MX, N4);
-      uint32_t e = NEG_OE, hoe_left = NEG_OE;
-      uint32_t diag = HF[tid].x;                              // old H - oe of cell 0
-      uint32_t* hrow = hmine + (size_t)n * bw * 32;
-      for (int b = 0; b < bw; ++b) {
-        uint2 up = make_uint2(NEG_OE, NEG_OE);
-        if (b + 1 < bw) up = HF[(b + 1) * THREADS + tid];
-        uint32_t f;
-        hrow[b * 32] = band_cell<HAS_N>(pa, pb, sel[(n + b) * THREADS + tid], diag, up.x, up.y, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
-        HF[b * THREADS + tid] = make_uint2(hoe_left, f);
-        diag = up.x;
-      }
-    }
-    walk_h_and_emit<HAS_N>(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> uint32_t { return hmine[((size_t)n * bw + b) * 32] & 0xFFFFu; });
-    if (haveB)
-      walk_h_and_emit<HAS_N>(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> uint32_t { return hmine[((size_t)n * bw + b) * 32] >> 16; });
+      walk_h_and_emit<HAS_N, true>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
   }
 }
 

@@ -4,6 +4,7 @@
 // that needs the GPU fails with UBU_SW_ERR_NO_DEVICE / UBU_SW_ERR_CUDA when it is not there.
 #include "sw_fwd16.cuh"
 #include "sw_tb.cuh"
+#include "sw_tbrect.cuh"
 #include "sw_post.cuh"
 
 #include <algorithm>
@@ -29,7 +30,9 @@ constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
 constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
-constexpr int TBS_THREADS = 32;                          // shared-memory-band traceback (CTAs per SM depend on the band cap)
+constexpr int TBR_THREADS = 64, TBR_GRID_PER_SM = 8;     // wide bands: systolic rectangle fill, three (rows, G, K) classes
+struct RectCfg { int rows, G, K; };
+const RectCfg kRectCfgs[3] = {{96, 8, 12}, {160, 8, 20}, {256, 16, 16}};
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
 constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
 
@@ -78,10 +81,10 @@ struct Slot {
   DevBuf<ubu_sw_result> d_res;
   DevBuf<unsigned int> d_ctr;            // [0..7] class counts, [8] cigar cursor, [9] error flags
   DevBuf<uint32_t> d_hstore;             // packed H of every band cell: [BW=8 | BW=16 | BW=32 | shared-memory band] regions
-  size_t h_off[6] = {0, 0, 0, 0, 0, 0};   // band 8 | 16 | 32 | shared-memory caps 0, 1, 2
+  size_t h_off[6] = {0, 0, 0, 0, 0, 0};   // band 8 | 16 | 32 | rectangle classes 0, 1, 2
   size_t ops_off[3] = {0, 0, 0};
-  SmemCaps caps{{0, 0, 0}};
-  int tbs_ctas[3] = {0, 0, 0};           // CTAs per SM of the three shared-memory band classes
+  RectCaps caps{{0, 0, 0}, {0, 0, 0}};
+  bool rect_on[3] = {false, false, false};
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
@@ -165,6 +168,35 @@ cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& 
     case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, st);
     UBU_FWD_CFGS(X)
 #undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int G, int K, bool HAS_N, bool DEF>
+cudaError_t launch_rect_t(int grid, const TbArgs& a, const uint32_t* list, const unsigned int* count, uint32_t* scratch, uint32_t* ops,
+                          int wcap, cudaStream_t st) {
+  constexpr int GP = TBR_THREADS / G;
+  const int sel_stride = ((wcap + 2 * G + 15) / 16) * 16;
+  const size_t smem = (size_t)GP * sel_stride * (HAS_N ? 4u : 2u);
+  auto kern = tb_rect_kernel<G, K, HAS_N, DEF, TBR_THREADS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, TBR_THREADS, smem, st>>>(a, list, count, scratch, ops, wcap, sel_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rect(int c, bool has_n, bool def, int grid, const TbArgs& a, const uint32_t* list, const unsigned int* count,
+                        uint32_t* scratch, uint32_t* ops, int wcap, cudaStream_t st) {
+  switch (c * 4 + (has_n ? 1 : 0) + (def ? 2 : 0)) {
+#define R(i, g, k) \
+    case i * 4: return launch_rect_t<g, k, false, false>(grid, a, list, count, scratch, ops, wcap, st); \
+    case i * 4 + 1: return launch_rect_t<g, k, true, false>(grid, a, list, count, scratch, ops, wcap, st); \
+    case i * 4 + 2: return launch_rect_t<g, k, false, true>(grid, a, list, count, scratch, ops, wcap, st); \
+    case i * 4 + 3: return launch_rect_t<g, k, true, true>(grid, a, list, count, scratch, ops, wcap, st);
+    R(0, 8, 12) R(1, 8, 20) R(2, 16, 16)
+#undef R
     default: return cudaErrorInvalidValue;
   }
 }
@@ -329,30 +361,31 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   {
     const int gbmax = gap_bound(h->sc, max_rows, 1);
     s.bw_cap = std::min(kMaxK + 2 * gbmax + 1, max_rows + 65535);
-    // widest band whose rows (H - oe, F: 2 x u32 per cell) and selectors fit the shared-memory kernel
-    const size_t selsz = s.any_n ? 4 : 2;
-    const long avail = (long)kMaxDynSmem - (long)max_rows * TBS_THREADS * (long)selsz;
-    long cap = avail > 0 ? avail / (long)(TBS_THREADS * (8 + selsz)) : 0;
-    s.smem_bw_cap = (int)std::max<long>(0, std::min<long>(cap, s.bw_cap));
-    s.caps.cap[0] = std::min(64, s.smem_bw_cap); s.caps.cap[1] = std::min(128, s.smem_bw_cap); s.caps.cap[2] = s.smem_bw_cap;
     const size_t reg_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
     s.h_off[0] = 0;
     s.h_off[1] = s.h_off[0] + reg_threads * (size_t)max_rows * 8;
     s.h_off[2] = s.h_off[1] + reg_threads * (size_t)max_rows * 16;
     s.h_off[3] = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
     size_t hwords = s.h_off[3], opwords = 0;
+    // wide bands: rectangle classes by read rows; width cap = rows + the largest gap budget those rows allow
+    s.smem_bw_cap = 0;
     for (int c = 0; c < 3; ++c) {
-      const int bc = s.caps.cap[c];
-      const size_t smem = (size_t)bc * TBS_THREADS * 8 + (size_t)(max_rows + bc) * TBS_THREADS * selsz;
-      s.tbs_ctas[c] = (bc > 32 && (c == 0 || bc > s.caps.cap[c - 1])) ? (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 0;
-      const size_t threads = (size_t)h->sm_count * s.tbs_ctas[c] * TBS_THREADS;
+      const RectCfg& rc_ = kRectCfgs[c];
+      const int rows = std::min(rc_.rows, max_rows);
+      int wcap = rows + gap_bound(h->sc, rows, 1);
+      wcap = std::min(((wcap + 15) / 16) * 16, 4096);
+      s.rect_on[c] = (c == 0 || max_rows > kRectCfgs[c - 1].rows) && s.bw_cap > 32;
+      s.caps.rows[c] = s.rect_on[c] ? rc_.rows : 0; s.caps.wcap[c] = s.rect_on[c] ? wcap : 0;
+      const size_t groups = (size_t)h->sm_count * TBR_GRID_PER_SM * (TBR_THREADS / rc_.G);
       s.h_off[3 + c] = hwords; s.ops_off[c] = opwords;
-      hwords += threads * (size_t)max_rows * (size_t)bc;
-      opwords += threads * (size_t)(2 * bc + max_rows + 8);
+      if (s.rect_on[c]) {
+        hwords += groups * (size_t)wcap * (size_t)(rc_.G * rc_.K);
+        opwords += (size_t)h->sm_count * TBR_GRID_PER_SM * TBR_THREADS * (size_t)(2 * wcap + 16);
+      }
     }
     CU(h, s.d_hstore.reserve(hwords));
     CU(h, s.d_ops.reserve(opwords + 8));
-    if (s.bw_cap > s.smem_bw_cap) {
+    {
       const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
       CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
     }
@@ -438,30 +471,16 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     }
     s.n_launches += 3;
   }
-  for (int c = 0; c < 3; ++c) {                       // shared-memory bands: narrow caps first, each on its own stream
-    if (!s.tbs_ctas[c]) continue;
-    const int bc = s.caps.cap[c];
-    const size_t selsz = s.any_n ? 4 : 2;
-    const size_t smem = (size_t)bc * TBS_THREADS * 8 + (size_t)(max_rows + bc) * TBS_THREADS * selsz;
-    const int grid = h->sm_count * s.tbs_ctas[c];
-    uint32_t* hs = s.d_hstore.p + s.h_off[3 + c];
-    uint32_t* ops = s.d_ops.p + s.ops_off[c];
-    if (s.any_n) {
-      auto k = tb_fill_smem_kernel<true, TBS_THREADS>;
-      if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, s.aux[2 + c]>>>(a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c, hs, ops, max_rows, bc);
-    } else {
-      auto k = tb_fill_smem_kernel<false, TBS_THREADS>;
-      if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      k<<<grid, TBS_THREADS, smem, s.aux[2 + c]>>>(a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c, hs, ops, max_rows, bc);
-    }
-    CU(h, cudaGetLastError()); ++s.n_launches;
+  for (int c = 0; c < 3; ++c) {                       // wide bands: rectangle classes, each on its own stream
+    if (!s.rect_on[c]) continue;
+    const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
+    CU(h, launch_rect(c, s.any_n, def, h->sm_count * TBR_GRID_PER_SM, a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c,
+                      s.d_hstore.p + s.h_off[3 + c], s.d_ops.p + s.ops_off[c], s.caps.wcap[c], s.aux[2 + c]));
+    ++s.n_launches;
   }
-  if (s.bw_cap > s.smem_bw_cap) {
-    tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
-                                                                              s.d_wide.p, max_rows, s.bw_cap);
-    CU(h, cudaGetLastError()); ++s.n_launches;
-  }
+  tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
+                                                                            s.d_wide.p, max_rows, s.bw_cap);
+  CU(h, cudaGetLastError()); ++s.n_launches;
   for (int k = 0; k < kAux; ++k) {                    // join
     CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
     CU(h, cudaStreamWaitEvent(st, s.ev_join[k], 0));
