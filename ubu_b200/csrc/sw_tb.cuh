@@ -150,19 +150,25 @@ __device__ __forceinline__ void emit_result(const TbArgs& a, uint32_t task, cons
 // band row n (n = i - i_first) for THIS task's half: bits 0-14 = H, bit 15 = diagonal does not reproduce H.
 // Rows above i_first are the zero boundary; cells left of column 1 were filled as H = 0.
 // USE_FLAG = false: the store holds H only and the diagonal test is made from the sequences (16 bases per load).
-template <bool HAS_N, bool USE_FLAG, class WordAt>
+// WB = cells fetched per round trip along the current diagonal (a multiple of 16 when !USE_FLAG).
+template <bool HAS_N, bool USE_FLAG, int WB, class WordAt>
 __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, const TaskView& t, const Band& g, int bw,
                                                 uint32_t* opbuf, WordAt word_at) {
   const int ma = a.sc.match, mm = a.sc.mismatch, open = a.sc.gap_open, ext = a.sc.gap_ext;
-  constexpr int WB = 8;                                   // cells served by one batch of independent loads
+  static_assert(USE_FLAG || WB % 16 == 0 || WB == 8, "sequence words cover 16 bases");
   // SPEC section 4: smallest row among the candidates that reaches S in column je
+  constexpr int SB = (WB > 8) ? 32 : 8;                   // batch of the candidate / gap scans
   int ie = 0;
-  for (int i0 = g.i_lo; i0 <= g.i_hi && !ie; i0 += WB) {
-    int v[WB];
+  for (int i0 = g.i_lo; i0 <= g.i_hi && !ie; i0 += SB) {
+    int v[SB];
 #pragma unroll
-    for (int u = 0; u < WB; ++u) v[u] = (i0 + u <= g.i_hi) ? (int)(word_at(i0 + u - g.i_first, g.je - i0 - u - g.d_lo) & 0x7FFFu) : -1;
+    for (int u = 0; u < SB; ++u) {                          // loads are unconditional (clamped) so that they all go out together
+      const int ii = min(i0 + u, g.i_hi);
+      v[u] = (int)(word_at(ii - g.i_first, g.je - ii - g.d_lo) & 0x7FFFu);
+      if (i0 + u > g.i_hi) v[u] = -1;
+    }
 #pragma unroll
-    for (int u = WB - 1; u >= 0; --u) if (v[u] == g.S) ie = i0 + u;
+    for (int u = SB - 1; u >= 0; --u) if (v[u] == g.S) ie = i0 + u;
   }
   if (ie == 0) { atomicOr(a.err_flag, 2u); return; }
   OpRuns o; o.init(opbuf);
@@ -176,12 +182,18 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
     // long diagonal runs, so one round trip to the H store serves up to WB steps
     uint32_t w[WB + 1];
 #pragma unroll
-    for (int k = 0; k <= WB; ++k) w[k] = (n - k >= 0) ? word_at(n - k, b) : 0u;
-    uint32_t xdiff = 0u, xn = 0u;                          // !USE_FLAG: base (i-1-k) vs (j-1-k) differ / involve N, at bit 2*(15-k) / (15-k)
-    if (!USE_FLAG) {
-      xdiff = load16(t.q, i - 16) ^ load16(t.r, j - 16);
-      xdiff = (xdiff | (xdiff >> 1)) & 0x55555555u;
-      if (HAS_N) { if (t.qn) xn |= load16n(t.qn, i - 16); if (t.rn) xn |= load16n(t.rn, j - 16); }
+    for (int k = 0; k <= WB; ++k) { w[k] = word_at(max(n - k, 0), b); if (n - k < 0) w[k] = 0u; }   // unconditional, clamped loads
+    // !USE_FLAG: word c covers steps k = 16c .. 16c+15: base (i-1-k) vs (j-1-k) differ / involve N, at bit 2*(15-(k%16)) / (15-(k%16))
+    constexpr int NXW = (WB + 15) / 16;
+    uint32_t xdiff[NXW], xn[NXW];
+#pragma unroll
+    for (int c = 0; c < NXW; ++c) {
+      xdiff[c] = 0u; xn[c] = 0u;
+      if (!USE_FLAG) {
+        xdiff[c] = load16(t.q, i - 16 - 16 * c) ^ load16(t.r, j - 16 - 16 * c);
+        xdiff[c] = (xdiff[c] | (xdiff[c] >> 1)) & 0x55555555u;
+        if (HAS_N) { if (t.qn) xn[c] |= load16n(t.qn, i - 16 - 16 * c); if (t.rn) xn[c] |= load16n(t.rn, j - 16 - 16 * c); }
+      }
     }
     bool stop = false;
 #pragma unroll
@@ -190,8 +202,8 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
         bool diag;
         if (USE_FLAG) diag = !(w[k] & 0x8000u);
         else {
-          const bool isn = HAS_N && ((xn >> (15 - k)) & 1u);
-          const int sk = isn ? 0 : (((xdiff >> (2 * (15 - k))) & 1u) ? mm : ma);
+          const bool isn = HAS_N && ((xn[k / 16] >> (15 - (k % 16))) & 1u);
+          const int sk = isn ? 0 : (((xdiff[k / 16] >> (2 * (15 - (k % 16)))) & 1u) ? mm : ma);
           diag = (i >= 1 && j >= 1) && ((int)(w[k + 1] & 0x7FFFu) + sk == h);
         }
         if (h > 0 && diag) { o.push(UBU_SW_CIGAR_M, 1u); ++n_m; --i; --j; h = (int)(w[k + 1] & 0x7FFFu); }
@@ -204,35 +216,46 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
     const int n2 = i - g.i_first, b2 = j - i - g.d_lo;
     if (i < 1 || j < 1 || n2 < 0 || b2 < 0 || b2 >= bw) { bad = true; break; }
     const int kcap = min(grem, (g.S - h - open) / ext);
-    int kbest = 0;
-    {   // read gap (I): largest k with H[i-k][j] - open - k*ext == h
-      const int kmax = min(kcap, min(n2, bw - 1 - b2));
-      for (int k0 = 1; k0 <= kmax; k0 += WB) {
-        int hv[WB];
+    // read gap (I): largest k with H[i-k][j] - open - k*ext == h;  window gap (D): same along the row; I has priority.
+    // The first SB candidates of BOTH directions are fetched in one round trip (the scans are latency-bound).
+    const int kmaxI = min(kcap, min(n2, bw - 1 - b2)), kmaxD = min(kcap, min(b2, j - 1));
+    int kI = 0, kD = 0;
+    {
+      int hi_[SB], hd_[SB];
 #pragma unroll
-        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? (int)(word_at(n2 - k0 - u, b2 + k0 + u) & 0x7FFFu) : -1;
+      for (int u = 0; u < SB; ++u) {
+        const int ui = min(1 + u, max(kmaxI, 0)), ud = min(1 + u, max(kmaxD, 0));     // clamped: every load is issued
+        hi_[u] = (int)(word_at(n2 - ui, b2 + ui) & 0x7FFFu); if (1 + u > kmaxI) hi_[u] = -1;
+        hd_[u] = (int)(word_at(n2, b2 - ud) & 0x7FFFu); if (1 + u > kmaxD) hd_[u] = -1;
+      }
 #pragma unroll
-        for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
+      for (int u = 0; u < SB; ++u) {
+        if (hi_[u] == h + open + (1 + u) * ext) kI = 1 + u;
+        if (hd_[u] == h + open + (1 + u) * ext) kD = 1 + u;
       }
     }
-    if (kbest) {
-      o.push(UBU_SW_CIGAR_I, (uint32_t)kbest); gap_bases += kbest; gap_cost += open + kbest * ext; grem -= kbest;
-      i -= kbest; h += open + kbest * ext;
+    for (int k0 = 1 + SB; k0 <= kmaxI; k0 += SB) {
+      int hv[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) { const int kk = min(k0 + u, kmaxI); hv[u] = (int)(word_at(n2 - kk, b2 + kk) & 0x7FFFu); if (k0 + u > kmaxI) hv[u] = -1; }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kI = k0 + u;
+    }
+    if (kI) {
+      o.push(UBU_SW_CIGAR_I, (uint32_t)kI); gap_bases += kI; gap_cost += open + kI * ext; grem -= kI;
+      i -= kI; h += open + kI * ext;
       continue;
     }
-    {   // window gap (D): largest k with H[i][j-k] - open - k*ext == h
-      const int kmax = min(kcap, min(b2, j - 1));
-      for (int k0 = 1; k0 <= kmax; k0 += WB) {
-        int hv[WB];
+    for (int k0 = 1 + SB; k0 <= kmaxD; k0 += SB) {
+      int hv[SB];
 #pragma unroll
-        for (int u = 0; u < WB; ++u) hv[u] = (k0 + u <= kmax) ? (int)(word_at(n2, b2 - k0 - u) & 0x7FFFu) : -1;
+      for (int u = 0; u < SB; ++u) { const int kk = min(k0 + u, kmaxD); hv[u] = (int)(word_at(n2, b2 - kk) & 0x7FFFu); if (k0 + u > kmaxD) hv[u] = -1; }
 #pragma unroll
-        for (int u = 0; u < WB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kbest = k0 + u;
-      }
+      for (int u = 0; u < SB; ++u) if (hv[u] == h + open + (k0 + u) * ext) kD = k0 + u;
     }
-    if (kbest) {
-      o.push(UBU_SW_CIGAR_D, (uint32_t)kbest); gap_bases += kbest; gap_cost += open + kbest * ext; grem -= kbest;
-      j -= kbest; h += open + kbest * ext;
+    if (kD) {
+      o.push(UBU_SW_CIGAR_D, (uint32_t)kD); gap_bases += kD; gap_cost += open + kD * ext; grem -= kD;
+      j -= kD; h += open + kD * ext;
       continue;
     }
     bad = true; break;
@@ -461,9 +484,9 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
         Hd[b] = hoe_left; Fv[b] = f;
       }
     }
-    walk_h_and_emit<HAS_N, true>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
+    walk_h_and_emit<HAS_N, true, 8>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
     if (haveB)
-      walk_h_and_emit<HAS_N, true>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
+      walk_h_and_emit<HAS_N, true, 8>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
   }
 }
 

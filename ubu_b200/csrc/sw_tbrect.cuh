@@ -160,10 +160,10 @@ tb_rect_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
       bd.i_first = 1; bd.rows = rg.i_hi; bd.c0 = 0; bd.gb = rg.gb;
       const int shift = (g == 0) ? 0 : 16;
       const int clo = rg.clo, dlo = rg.d_lo;
-      walk_h_and_emit<HAS_N, false>(a, (g == 0) ? tA : tB, tv, bd, bd.bw, opbuf, [&](int n, int b) -> uint32_t {
+      walk_h_and_emit<HAS_N, false, 16>(a, (g == 0) ? tA : tB, tv, bd, bd.bw, opbuf, [&](int n, int b) -> uint32_t {
         const int row0 = n, kk = (n + 1) + dlo + b - clo;         // row i = n + 1 (i_first = 1), column j = i + d_lo + b
-        if (kk < 0) return 0u;                                     // left of the rectangle: zero boundary
-        return (__ldcg(block + (size_t)kk * RS + row0) >> shift) & 0xFFFFu;
+        const uint32_t v = (__ldcg(block + (size_t)max(kk, 0) * RS + row0) >> shift) & 0xFFFFu;   // unconditional, clamped
+        return kk < 0 ? 0u : v;                                    // left of the rectangle: zero boundary
       });
     }
     __syncwarp();
