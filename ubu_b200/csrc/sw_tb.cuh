@@ -157,7 +157,7 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
   const int ma = a.sc.match, mm = a.sc.mismatch, open = a.sc.gap_open, ext = a.sc.gap_ext;
   static_assert(USE_FLAG || WB % 16 == 0 || WB == 8, "sequence words cover 16 bases");
   // SPEC section 4: smallest row among the candidates that reaches S in column je
-  constexpr int SB = (WB > 8) ? 32 : 8;                   // batch of the candidate / gap scans
+  constexpr int SB = (WB > 8) ? 16 : 8;                   // batch of the candidate / gap scans
   int ie = 0;
   for (int i0 = g.i_lo; i0 <= g.i_hi && !ie; i0 += SB) {
     int v[SB];
