@@ -167,3 +167,15 @@ def test_full_size_cfg2_properties(aligner):
     ores, ocig = O.align_batch(q, wi, None, nthreads=8)
     for j, k in enumerate(pick):
         assert all(int(r[int(k)][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(int(k)) == ocig[j]
+
+
+def test_extreme_scoring_reaches_the_scalar_last_resort():
+    """match 31 / ext 1 lets a low score afford thousands of gap bases: the band outgrows every packed class."""
+    rng = np.random.default_rng(2)
+    reads = ["A" * 256, "".join(rng.choice(list("ACGT"), size=200)), "ACGT" * 50]
+    wins = ["C" * 8000 + "AAA" + "C" * 50, "".join(rng.choice(list("ACGT"), size=7000)), "G" * 5000 + "ACGTACGTAC" + "G" * 100]
+    r, w = U.pack_texts(reads), U.pack_texts(wins)
+    params = (31, 0, 0, 1)
+    with U.SwAligner(*params) as a:
+        al = a.align(r, w)
+    check_against_oracle(al, r, w, None, params)

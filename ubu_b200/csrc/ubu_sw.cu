@@ -85,6 +85,7 @@ struct Slot {
   size_t ops_off[3] = {0, 0, 0};
   RectCaps caps{{0, 0, 0}, {0, 0, 0}};
   bool rect_on[3] = {false, false, false};
+  int tbw_grid = 1;
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
@@ -386,8 +387,14 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     CU(h, s.d_hstore.reserve(hwords));
     CU(h, s.d_ops.reserve(opwords + 8));
     {
-      const size_t workers = (size_t)h->sm_count * TBW_GRID_PER_SM * TBW_THREADS;
-      CU(h, s.d_wide.reserve(workers * tb_wide_scratch_bytes(max_rows, s.bw_cap)));
+      // the scalar last resort only sees bands no other class takes (extreme scoring / very long windows): its band can be
+      // as wide as the whole window, so its scratch is capped at 2 GB by running fewer CTAs
+      int wcap_all = 0;
+      for (uint32_t w = 0; w < wins->count; ++w) wcap_all = std::max(wcap_all, (int)wins->len[w]);
+      s.bw_cap = std::min(s.bw_cap, max_rows + wcap_all);
+      const size_t per = tb_wide_scratch_bytes(max_rows, s.bw_cap) * TBW_THREADS;
+      s.tbw_grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->sm_count * TBW_GRID_PER_SM, ((size_t)2 << 30) / std::max<size_t>(per, 1)));
+      CU(h, s.d_wide.reserve((size_t)s.tbw_grid * per));
     }
   }
 
@@ -478,7 +485,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
                       s.d_hstore.p + s.h_off[3 + c], s.d_ops.p + s.ops_off[c], s.caps.wcap[c], s.aux[2 + c]));
     ++s.n_launches;
   }
-  tb_wide_kernel<<<h->sm_count * TBW_GRID_PER_SM, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
+  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
                                                                             s.d_wide.p, max_rows, s.bw_cap);
   CU(h, cudaGetLastError()); ++s.n_launches;
   for (int k = 0; k < kAux; ++k) {                    // join
