@@ -86,6 +86,7 @@ struct Slot {
   RectCaps caps{{0, 0, 0}, {0, 0, 0}};
   bool rect_on[3] = {false, false, false};
   int tbw_grid = 1;
+  bool pre_queued = false; size_t pre_words = 0;   // early device->host copies queued by submit()
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   PinBuf<uint32_t> h_order;
@@ -338,7 +339,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   int rc = validate_seqs(reads); if (rc) return rc;
   rc = validate_seqs(wins); if (rc) return rc;
   if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
-  s.staged = false; s.ran = false;
+  s.staged = false; s.ran = false; s.pre_queued = false;
   s.n_tasks = reads->count;
   s.have_idx = idx != nullptr;
   s.reads_n = reads->nmask != nullptr; s.wins_n = wins->nmask != nullptr;
@@ -497,12 +498,39 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   return UBU_SW_OK;
 }
 
+// submit(): the device->host copies that do not depend on the CIGAR count are queued right behind the kernels
+// (records, counters, and a first slice of the pool sized for ~2 ops per task), so wait() usually needs one sync.
+int enqueue_early_d2h(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size_t pool_cap) {
+  s.pre_words = 0;
+  if (s.n_tasks == 0 || !out) return UBU_SW_OK;
+  cudaStream_t st = s.stream;
+  CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(out, s.d_res.p, sizeof(ubu_sw_result) * s.n_tasks, cudaMemcpyDeviceToHost, st));
+  const size_t guess = std::min<size_t>(std::min<size_t>(pool_cap, s.cig_cap), (size_t)2 * s.n_tasks + 64);
+  if (pool && guess) { CU(h, cudaMemcpyAsync(pool, s.d_cig.p, sizeof(uint32_t) * guess, cudaMemcpyDeviceToHost, st)); s.pre_words = guess; }
+  s.pre_queued = true;
+  return UBU_SW_OK;
+}
+
 int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size_t pool_cap, size_t* used) {
   if (!s.ran) return UBU_SW_ERR_ARG;
   if (used) *used = 0;
   if (s.n_tasks == 0) return UBU_SW_OK;
   if (!out) return UBU_SW_ERR_ARG;
   cudaStream_t st = s.stream;
+  if (s.pre_queued) {                  // fast path of wait(): everything may already be on its way
+    s.pre_queued = false;
+    CU(h, cudaStreamSynchronize(st));
+    const unsigned int need = s.h_ctr.p[8], err = s.h_ctr.p[9];
+    if (!err && need <= pool_cap && (need == 0 || pool)) {
+      if (need > s.pre_words) {
+        CU(h, cudaMemcpyAsync(pool + s.pre_words, s.d_cig.p + s.pre_words, sizeof(uint32_t) * (need - s.pre_words), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+      }
+      if (used) *used = need;
+      return UBU_SW_OK;
+    }
+  }
   for (int attempt = 0;; ++attempt) {
     CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
@@ -660,6 +688,7 @@ int ubu_sw_submit(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs*
   Slot& s = h->slots[slot];
   int rc = do_stage(h, s, reads, windows, pair_ref_idx); if (rc) return rc;
   rc = do_run(h, s); if (rc) return rc;
+  rc = enqueue_early_d2h(h, s, out, cigar_pool, cigar_pool_cap); if (rc) return rc;
   s.out = out; s.pool = cigar_pool; s.pool_cap = cigar_pool_cap; s.pending = true;
   h->next_slot = (slot + 1) % h->n_slots;
   *ticket = slot;
