@@ -11,6 +11,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the C-ABI library and the oracle are built in-tree; build them if a fresh checkout has not run build() yet
+    try:
+        from ubu_b200 import build as B
+
+        if not os.path.exists(B.LIB):
+            B.build()
+    except Exception as e:  # the ABI tests will then fail loudly with the loader's message
+        sys.stderr.write(f"[conftest] could not build libubu_sw.so: {e}\n")
 
 
 def _has_gpu() -> bool:

@@ -179,3 +179,21 @@ def test_extreme_scoring_reaches_the_scalar_last_resort():
     with U.SwAligner(*params) as a:
         al = a.align(r, w)
     check_against_oracle(al, r, w, None, params)
+
+
+def test_very_long_windows_use_the_global_selector_scratch(aligner):
+    """Short reads against windows too long for the shared-memory selector array (76 bp vs 20-60 kb)."""
+    rng = np.random.default_rng(8)
+    wins, reads = [], []
+    for W in (20000, 33000, 60000, 65535):
+        w = "".join(rng.choice(list("ACGT"), size=W))
+        wins.append(w)
+        s = int(rng.integers(0, W - 100))
+        r = list(w[s:s + 76]); r[10] = "A" if r[10] != "A" else "C"
+        reads.append("".join(r))
+        reads.append(w[W - 76:])                       # alignment ending in the last column
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    idx = np.array([0, 0, 1, 1, 2, 2, 3, 3], dtype=np.uint32)
+    al = aligner.align(rs, ws, idx)
+    check_against_oracle(al, rs, ws, idx)
+    assert int(al.results[7]["ref_end"]) == 65535 and al.cigar_string(7) == "76M"

@@ -44,16 +44,19 @@ namespace ubu {
 #ifndef UBU_FWD_UNROLL
 #define UBU_FWD_UNROLL 2
 #endif
-template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
+// SEL_GLOBAL = true keeps the per-column selectors in a global scratch instead of shared memory: used only when the
+// windows of a launch are too long for shared memory (the loads are sequential 2-byte reads, served by L1).
+template <int G, int K, bool HAS_N, bool DEFAULT_SC, bool SEL_GLOBAL, int THREADS>
 __global__ void __launch_bounds__(THREADS, UBU_FWD_MIN_BLOCKS)
 sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
                 const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks, Scoring sc,
-                FwdOut* __restrict__ out, int sel_stride) {
+                FwdOut* __restrict__ out, int sel_stride, void* __restrict__ gsel) {
   static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide the warp");
   constexpr int GP = THREADS / G;
   using SelT = typename SelType<HAS_N>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SelT* sel_all = reinterpret_cast<SelT*>(smem_raw);
+  SelT* sel_all = SEL_GLOBAL ? reinterpret_cast<SelT*>(gsel) + (size_t)blockIdx.x * (THREADS / G) * sel_stride
+                             : reinterpret_cast<SelT*>(smem_raw);
   __shared__ int s_wmax;
 
   const int tid = threadIdx.x;

@@ -67,7 +67,7 @@ struct PinBuf {
 };
 
 constexpr int kAux = 5;
-struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; };
+struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; };   // selectors go to global scratch when they do not fit shared memory
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -89,6 +89,7 @@ struct Slot {
   bool pre_queued = false; size_t pre_words = 0;   // early device->host copies queued by submit()
   DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
+  DevBuf<unsigned char> d_gsel;          // per-column selectors of forward launches with very long windows
   PinBuf<uint32_t> h_order;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
@@ -144,30 +145,35 @@ size_t fwd_smem_bytes(int cfg, bool has_n, int wmax) {
 
 template <int G, int K, bool HAS_N, bool DEF>
 cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
-                         const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+                         const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, cudaStream_t st) {
   constexpr int GP = FWD_THREADS / G;
   const int stride = sel_stride_for(L.wmax, G);
   const size_t smem = (size_t)GP * stride * (HAS_N ? 4u : 2u);
-  auto kern = sw_fwd16_kernel<G, K, HAS_N, DEF, FWD_THREADS>;
+  const uint32_t pairs = L.n_slots / 2;
+  const uint32_t grid = (pairs + GP - 1) / GP;
+  const uint32_t* ord = order ? order + L.begin : nullptr;
+  if (smem > kMaxDynSmem) {            // long windows: selectors in global scratch (sized by the caller)
+    sw_fwd16_kernel<G, K, HAS_N, DEF, true, FWD_THREADS><<<grid, FWD_THREADS, 0, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, gsel);
+    return cudaGetLastError();
+  }
+  auto kern = sw_fwd16_kernel<G, K, HAS_N, DEF, false, FWD_THREADS>;
   if (smem > 48 * 1024) {      // per device, so set on every large launch (cheap)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return e;
   }
-  const uint32_t pairs = L.n_slots / 2;
-  const uint32_t grid = (pairs + GP - 1) / GP;
-  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, order ? order + L.begin : nullptr, L.n_slots, L.n_tasks, sc, out, stride);
+  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
-                       const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+                       const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, cudaStream_t st) {
   const bool def = sc.match == 1 && sc.mismatch == -3 && sc.gap_open == 5 && sc.gap_ext == 2;
   switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
 #define X(i, l, g, k) \
-    case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, st); \
-    case i * 4 + 1: return launch_fwd_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, st); \
-    case i * 4 + 2: return launch_fwd_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, st); \
-    case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, st);
+    case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, gsel, st); \
+    case i * 4 + 1: return launch_fwd_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, gsel, st); \
+    case i * 4 + 2: return launch_fwd_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, gsel, st); \
+    case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, gsel, st);
     UBU_FWD_CFGS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -245,7 +251,6 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)lmax + 7u) / 8u > reads->nmask_bytes);
       if (wins->nmask) for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->nmask_off[w] + ((uint32_t)wmax + 7u) / 8u > wins->nmask_bytes);
       if (bad) return UBU_SW_ERR_ARG;
-      if (fwd_smem_bytes(c1, false, wmax) > kMaxDynSmem) return UBU_SW_ERR_TOO_LONG;
       s.lmax = lmax;
       s.n_slots = (n + 1u) & ~1u;
       s.identity_order = true;
@@ -312,7 +317,6 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       std::stable_sort(lo, lo + cnt[b], [&](uint32_t x, uint32_t y) { return (s.tmp_keys[x] & 0xFFFFu) < (s.tmp_keys[y] & 0xFFFFu); });
     }
     const int cfg = b / 2; const bool has_n = b & 1;
-    if (fwd_smem_bytes(cfg, has_n, wmaxv[b]) > kMaxDynSmem) return UBU_SW_ERR_TOO_LONG;
     // split a bucket whose widths vary a lot so that short windows do not pay the long ones' shared memory
     uint32_t beg = 0; const uint32_t total = (cnt[b] + 1u) & ~1u;
     while (beg < total) {
@@ -348,6 +352,15 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   rc = plan_batch(h, s, reads, wins, idx); if (rc) return rc;
 
   const uint32_t n = s.n_tasks, nw = wins->count;
+  {   // launches whose selectors do not fit shared memory keep them in a global scratch (one launch at a time on the stream)
+    size_t need = 0;
+    for (const FwdLaunch& L : s.launches) {
+      const FwdCfg& c = kFwdCfgs[L.cfg];
+      const size_t gp = FWD_THREADS / c.G, stride = (size_t)sel_stride_for(L.wmax, c.G), selsz = L.has_n ? 4 : 2;
+      if (gp * stride * selsz > kMaxDynSmem) need = std::max(need, (((size_t)L.n_slots / 2 + gp - 1) / gp) * gp * stride * selsz);
+    }
+    if (need) CU(h, s.d_gsel.reserve(need + 64));
+  }
   CU(h, s.d_rp.reserve(reads->packed_bytes + 16)); CU(h, s.d_roff.reserve(n)); CU(h, s.d_rlen.reserve(n));
   CU(h, s.d_wp.reserve(wins->packed_bytes + 16)); CU(h, s.d_woff.reserve(nw)); CU(h, s.d_wlen.reserve(nw));
   if (s.reads_n) { CU(h, s.d_rn.reserve(reads->nmask_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
@@ -432,7 +445,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
   const uint32_t* d_order = s.identity_order ? nullptr : s.d_order.p;
   for (const FwdLaunch& L : s.launches) {
-    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, st));
+    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, st));
     ++s.n_launches;
   }
   CU(h, cudaEventRecord(s.ev[1], st));
@@ -621,7 +634,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
     s.d_roff.release(); s.d_rnoff.release(); s.d_woff.release(); s.d_wnoff.release(); s.d_idx.release();
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
-    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release();
+    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release(); s.d_gsel.release();
     s.h_order.release(); s.h_ctr.release();
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
