@@ -20,7 +20,10 @@ namespace {
 
 // ---- length classes of the packed 16-bit forward kernel: rows capacity = G*K -------------------
 struct FwdCfg { int lmax, G, K; };
-constexpr int FWD_THREADS = 64;
+#ifndef UBU_FWD_THREADS
+#define UBU_FWD_THREADS 64
+#endif
+constexpr int FWD_THREADS = UBU_FWD_THREADS;
 #define UBU_FWD_CFGS(X) X(0, 32, 4, 8) X(1, 48, 4, 12) X(2, 64, 4, 16) X(3, 76, 4, 19) X(4, 80, 4, 20) X(5, 104, 8, 13) \
   X(6, 128, 8, 16) X(7, 152, 8, 19) X(8, 160, 8, 20) X(9, 208, 16, 13) X(10, 256, 16, 16)
 #define X(i, l, g, k) {l, g, k},
@@ -93,13 +96,13 @@ struct Slot {
   PinBuf<uint32_t> h_order;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
-  std::vector<uint32_t> tmp_keys, tmp_idx;
+  std::vector<uint32_t> tmp_keys;
   // staged batch
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
   bool any_n = false, have_idx = false, reads_n = false, wins_n = false;
   bool identity_order = false;           // uniform batch: tasks run in input order, no order array at all
-  int lmax = 0, bw_cap = 0, smem_bw_cap = 0;
+  int lmax = 0, bw_cap = 0;
   unsigned int cig_cap = 0;
   int n_launches = 0;
   // submit()/wait() bookkeeping
@@ -138,10 +141,6 @@ int cfg_of_len(int L) {
 
 int sel_stride_for(int wmax, int G) { return ((wmax + 2 * G + 63) / 64) * 64 + G; }
 
-size_t fwd_smem_bytes(int cfg, bool has_n, int wmax) {
-  const FwdCfg& c = kFwdCfgs[cfg];
-  return (size_t)(FWD_THREADS / c.G) * (size_t)sel_stride_for(wmax, c.G) * (has_n ? 4u : 2u);
-}
 
 template <int G, int K, bool HAS_N, bool DEF>
 cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
@@ -383,7 +382,6 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     s.h_off[3] = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
     size_t hwords = s.h_off[3], opwords = 0;
     // wide bands: rectangle classes by read rows; width cap = rows + the largest gap budget those rows allow
-    s.smem_bw_cap = 0;
     for (int c = 0; c < 3; ++c) {
       const RectCfg& rc_ = kRectCfgs[c];
       const int rows = std::min(rc_.rows, max_rows);
