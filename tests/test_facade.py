@@ -109,3 +109,51 @@ def test_device_writes_the_same_sam_as_the_oracle_stand_in(tmp_path):
     _, dev = run(tmp_path / "a", reads, contigs, align_fn=None)
     _, ora = run(tmp_path / "b", reads, contigs)
     assert dev == ora
+
+
+CLI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "ubu_aligner")
+
+
+def _build_cli():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(CLI):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, os.path.join(root, "host", "ubu_aligner_main.cpp"),
+                        os.path.join(root, "host", "aligner.cpp"), "-L" + os.path.join(root, "ubu_b200"), "-lubu_sw",
+                        "-Wl,-rpath,$ORIGIN/../ubu_b200"], check=True)
+
+
+def test_cpp_host_cli_fails_like_the_reference_without_its_inputs(tmp_path):
+    """host/aligner.cpp mirrors Aligner.java's names and error behaviour (RuntimeException -> message + exit 1)."""
+    import subprocess
+    _build_cli()
+    r = subprocess.run([CLI, "shortAlign", str(tmp_path / "missing.fa"), "x.fq", str(tmp_path / "o.sam")], capture_output=True, text=True)
+    assert r.returncode == 1 and "reference not found" in r.stderr
+    assert subprocess.run([CLI], capture_output=True).returncode == 2
+
+
+@pytest.mark.gpu
+def test_cpp_host_writes_the_same_sam_as_the_python_facade(tmp_path):
+    import subprocess
+    _build_cli()
+    rng = np.random.default_rng(14)
+    contigs = [(f"ctg{k}", "".join(rng.choice(list("ACGTN"), p=[.245, .245, .245, .245, .02], size=int(rng.integers(200, 600))))) for k in range(4)]
+    contigs.append(("dup", contigs[0][1]))
+    reads = []
+    for k in range(150):
+        c = contigs[int(rng.integers(0, 4))][1]
+        s = int(rng.integers(0, len(c) - 110))
+        r = list(c[s:s + int(rng.integers(40, 100))])
+        for p in range(len(r)):
+            if rng.random() < 0.04:
+                r[p] = "ACGT"[int(rng.integers(0, 4))]
+        if rng.random() < 0.2:
+            del r[len(r) // 2]
+        r = "".join(r)
+        reads.append((f"read{k}", U.reverse_complement(r) if rng.random() < 0.5 else r))
+    reads.append(("junk", "N" * 30))
+    ref, fq = write_inputs(tmp_path, reads, contigs)
+    a = Aligner(ref, 1); a.shortAlign(fq, str(tmp_path / "py.sam")); a.close()
+    r = subprocess.run([CLI, "shortAlign", ref, fq, str(tmp_path / "cpp.sam")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "py.sam").read() == open(tmp_path / "cpp.sam").read()
