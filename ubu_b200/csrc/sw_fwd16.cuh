@@ -91,35 +91,60 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
   const int oe = sc.gap_open + sc.gap_ext;
   const uint32_t mmb = (uint32_t)(sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(sc.match + oe) & 0xFFu;
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
+  // The prologue is written for latency: a warp that is not yet in the sweep cannot feed the ALU pipe, so everything is
+  // fetched 16 bases per pair of 32-bit loads (load16) and the loads of several chunks are issued before any is used.
   uint32_t profA[K], profB[K];
+  {
+    constexpr int NQ = (K + 15) / 16;
+    uint32_t qa[NQ], qb[NQ], na[NQ], nb[NQ];
 #pragma unroll
-  for (int r = 0; r < K; ++r) {
-    const int row = g * K + r;
-    uint32_t pa = 0x80808080u, pb = 0x80808080u;          // padding row: -128 against every base
-    if (row < LA) { pa = MM4 ^ (MX << (8u * base2(qA, row))); if (qnA && nbit(qnA, row)) pa = N4; }
-    if (row < LB) { pb = MM4 ^ (MX << (8u * base2(qB, row))); if (qnB && nbit(qnB, row)) pb = N4; }
-    profA[r] = pa; profB[r] = pb;
-  }
-
-  // ---- per-column PRMT selectors (shared memory), index = column + G ----------------------
-  SelT* sel = sel_all + (size_t)grp * sel_stride;
-  // one byte of each window = 4 columns = 4 selectors per trip (sel_stride and G are multiples of 4)
-  for (int q4 = g; q4 < sel_stride / 4; q4 += G) {
-    const int c0 = 4 * q4 - G;                              // first column of this quad (byte c0 / 4 of the window)
-    uint32_t byA = 0u, byB = 0u, nA = 0u, nB = 0u;
-    if (c0 >= 0 && c0 < WA) { byA = rA[c0 >> 2]; if (HAS_N && rnA) nA = (uint32_t)(rnA[c0 >> 3] >> (c0 & 4)) & 15u; }
-    if (c0 >= 0 && c0 < WB) { byB = rB[c0 >> 2]; if (HAS_N && rnB) nB = (uint32_t)(rnB[c0 >> 3] >> (c0 & 4)) & 15u; }
-    SelT out4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + j;
-      uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;             // padding column: sign-replicate selectors
-      if (c >= 0 && c < WA) { const uint32_t b = (byA >> (2 * j)) & 3u; lo = b | ((b | 8u) << 4); if (HAS_N && ((nA >> j) & 1u)) nf |= 0x00800000u; }
-      if (c >= 0 && c < WB) { const uint32_t b = ((byB >> (2 * j)) & 3u) + 4u; hi = b | ((b | 8u) << 4); if (HAS_N && ((nB >> j) & 1u)) nf |= 0x80000000u; }
-      out4[j] = (SelT)(lo | (hi << 8) | nf);
+    for (int c = 0; c < NQ; ++c) {
+      const int r0 = g * K + 16 * c;
+      qa[c] = (r0 < LA) ? load16(qA, r0) : 0u; qb[c] = (r0 < LB) ? load16(qB, r0) : 0u;
+      na[c] = (qnA && r0 < LA) ? load16n(qnA, r0) : 0u; nb[c] = (qnB && r0 < LB) ? load16n(qnB, r0) : 0u;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sel[4 * q4 + j] = out4[j];
+    for (int r = 0; r < K; ++r) {
+      const int row = g * K + r;
+      uint32_t pa = 0x80808080u, pb = 0x80808080u;          // padding row: -128 against every base
+      if (row < LA) { pa = MM4 ^ (MX << (8u * ((qa[r / 16] >> (2 * (r % 16))) & 3u))); if ((na[r / 16] >> (r % 16)) & 1u) pa = N4; }
+      if (row < LB) { pb = MM4 ^ (MX << (8u * ((qb[r / 16] >> (2 * (r % 16))) & 3u))); if ((nb[r / 16] >> (r % 16)) & 1u) pb = N4; }
+      profA[r] = pa; profB[r] = pb;
+    }
+  }
+
+  // ---- per-column PRMT selectors (shared memory or global scratch), index = column + G ----------------------
+  SelT* sel = sel_all + (size_t)grp * sel_stride;
+  {
+    constexpr int CH = 4;                                   // chunks of 16 columns fetched together
+    const int nch = (sel_stride + 15) / 16;
+    for (int cb = g; cb < nch; cb += G * CH) {
+      uint32_t wa[CH], wb[CH], fa[CH], fb[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int c0 = 16 * (cb + q * G) - G;               // first column of the chunk
+        const bool on = cb + q * G < nch;
+        wa[q] = (on && rA && c0 < WA && c0 + 16 > 0) ? load16(rA, c0) : 0u;   // rA == nullptr: no task in this half
+        wb[q] = (on && rB && c0 < WB && c0 + 16 > 0) ? load16(rB, c0) : 0u;
+        fa[q] = (HAS_N && rnA && on && c0 < WA && c0 + 16 > 0) ? load16n(rnA, c0) : 0u;
+        fb[q] = (HAS_N && rnB && on && c0 < WB && c0 + 16 > 0) ? load16n(rnB, c0) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int ch = cb + q * G;
+        if (ch < nch) {
+          const int c0 = 16 * ch - G;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int c = c0 + u;
+            uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;       // padding column: sign-replicate selectors
+            if (c >= 0 && c < WA) { lo = ((wa[q] >> (2 * u)) & 3u) * 0x11u + 0x80u; if (HAS_N && ((fa[q] >> u) & 1u)) nf |= 0x00800000u; }
+            if (c >= 0 && c < WB) { hi = ((wb[q] >> (2 * u)) & 3u) * 0x11u + 0xC4u; if (HAS_N && ((fb[q] >> u) & 1u)) nf |= 0x80000000u; }
+            if (16 * ch + u < sel_stride) sel[16 * ch + u] = (SelT)(lo | (hi << 8) | nf);
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   if (g == 0) atomicMax(&s_wmax, max(WA, WB));
