@@ -197,3 +197,70 @@ def test_very_long_windows_use_the_global_selector_scratch(aligner):
     al = aligner.align(rs, ws, idx)
     check_against_oracle(al, rs, ws, idx)
     assert int(al.results[7]["ref_end"]) == 65535 and al.cigar_string(7) == "76M"
+
+
+# ---- pairs that share their window: the query-profile forward kernel (csrc/sw_fwd16s.cuh) --------------------------------
+@pytest.mark.parametrize("L,W", [(76, 500), (100, 1000), (150, 2000), (250, 700), (33, 200), (50, 300), (128, 64), (208, 900)])
+def test_shared_window_pairs(aligner, L, W):
+    w = WL.uniform("sh", 601, L, W, seed=31 + L, paired=True, sub_rate=0.03, indel_rate=0.01, geom_p=0.4)      # odd count: last pair is half empty
+    al = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    check_against_oracle(al, w.reads, w.windows, w.pair_ref_idx)
+
+
+def test_shared_window_pairs_with_n(aligner):
+    base = WL.uniform("shn", 500, 76, 500, seed=4, paired=True, keep_codes=True)
+    w = WL.with_n(base, rate=0.02)
+    al = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    check_against_oracle(al, w.reads, w.windows, w.pair_ref_idx)
+
+
+@pytest.mark.parametrize("params", [(2, -1, 3, 1), (5, -4, 10, 1), (3, 0, 2, 2), (1, -9, 1, 1)])
+def test_shared_window_pairs_other_scoring(params):
+    w = WL.uniform("shp", 400, 90, 400, seed=22, paired=True, sub_rate=0.05, indel_rate=0.02, geom_p=0.4)
+    with U.SwAligner(*params) as a:
+        al = a.align(w.reads, w.windows, w.pair_ref_idx)
+    check_against_oracle(al, w.reads, w.windows, w.pair_ref_idx, params)
+
+
+def test_shared_window_ragged_reads_and_many_reads_per_window(aligner):
+    """Reads of different lengths (one length class) in a pair, windows of different lengths, and reads of one window
+    scattered over the batch (the planner groups them by window)."""
+    rng = np.random.default_rng(12)
+    wins = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(90, 700)))) for _ in range(40)]
+    reads, idx = [], []
+    for k in range(500):
+        wi = int(rng.integers(0, len(wins)))
+        w = wins[wi]
+        L = int(rng.integers(65, 77))                   # one length class (<= 76 rows)
+        s = int(rng.integers(0, max(len(w) - L, 1)))
+        r = list(w[s:s + L]) + list(rng.choice(list("ACGT"), size=max(0, L - len(w[s:s + L]))))
+        for p in rng.integers(0, L, size=2):
+            r[p] = "ACGT"[int(rng.integers(0, 4))]
+        reads.append("".join(r)); idx.append(wi)
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    idx = np.array(idx, dtype=np.uint32)
+    al = aligner.align(rs, ws, idx)
+    check_against_oracle(al, rs, ws, idx)
+    # same reads, every window the same length: the uniform-batch plan with its counting sort by window
+    wins2 = ["".join(rng.choice(list("ACGT"), size=400)) for _ in range(40)]
+    reads2 = []
+    for k in range(500):
+        w = wins2[int(idx[k])]
+        s = int(rng.integers(0, 400 - 76))
+        r = list(w[s:s + 76]); r[int(rng.integers(0, 76))] = "A"
+        reads2.append("".join(r))
+    rs2, ws2 = U.pack_texts(reads2), U.pack_texts(wins2)
+    al2 = aligner.align(rs2, ws2, idx)
+    check_against_oracle(al2, rs2, ws2, idx)
+
+
+def test_shared_window_kernel_equals_general_kernel(aligner, monkeypatch):
+    """The two forward kernels must give identical records on the same batch (UBU_NO_SHARED_WIN=1 forces the general one)."""
+    w = WL.uniform("eq", 20_000, 76, 500, seed=77, paired=True, sub_rate=0.04, indel_rate=0.01)
+    a1 = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    monkeypatch.setenv("UBU_NO_SHARED_WIN", "1")
+    a2 = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    monkeypatch.delenv("UBU_NO_SHARED_WIN")
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(a1.results[f], a2.results[f]), f
+    assert all(a1.cigar(k) == a2.cigar(k) for k in range(0, len(a1), 37))

@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "ubu_sw.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("ubu_sw.cu", "sw_common.cuh", "sw_fwd16.cuh", "sw_tb.cuh", "sw_tbrect.cuh", "sw_post.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("ubu_sw.cu", "sw_common.cuh", "sw_fwd16.cuh", "sw_fwd16s.cuh", "sw_tb.cuh", "sw_tbrect.cuh", "sw_post.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "ubu_sw.h")
 ]
 LIB = os.path.join(HERE, "libubu_sw.so")

@@ -44,6 +44,43 @@ namespace ubu {
 #ifndef UBU_FWD_UNROLL
 #define UBU_FWD_UNROLL 2
 #endif
+// Group arg-max of the forward sweep and the FwdOut records of the pair: candidates are ordered by
+// (score, smaller column, smaller lane), which is SPEC.md section 4 at lane granularity.
+template <int G, int K>
+__device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA, int stepB, int g, uint32_t tA, uint32_t tB, int LA, int LB,
+                                                       FwdOut* __restrict__ out) {
+  const int scA = (int)(int16_t)(best & 0xFFFFu), scB = (int)(int16_t)(best >> 16);
+  unsigned long long keyA = 0ull, keyB = 0ull;
+  if (scA > 0) keyA = ((unsigned long long)scA << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepA - g + 1)) << 8) | (unsigned long long)(31 - g);
+  if (scB > 0) keyB = ((unsigned long long)scB << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepB - g + 1)) << 8) | (unsigned long long)(31 - g);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const unsigned long long oa = __shfl_xor_sync(0xffffffffu, keyA, o, G);
+    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, keyB, o, G);
+    keyA = oa > keyA ? oa : keyA; keyB = ob > keyB ? ob : keyB;
+  }
+  if (g == 0) {
+    if (tA != 0xFFFFFFFFu) {
+      FwdOut o = {0, 0, 0, 0};
+      if (keyA) {
+        const int lane = 31 - (int)(keyA & 0xFFu);
+        o.score = (int)(keyA >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyA >> 8) & 0xFFFFu));
+        o.i_lo = lane * K + 1; o.i_hi = min(LA, lane * K + K);
+      }
+      out[tA] = o;
+    }
+    if (tB != 0xFFFFFFFFu) {
+      FwdOut o = {0, 0, 0, 0};
+      if (keyB) {
+        const int lane = 31 - (int)(keyB & 0xFFu);
+        o.score = (int)(keyB >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyB >> 8) & 0xFFFFu));
+        o.i_lo = lane * K + 1; o.i_hi = min(LB, lane * K + K);
+      }
+      out[tB] = o;
+    }
+  }
+}
+
 // SEL_GLOBAL = true keeps the per-column selectors in a global scratch instead of shared memory: used only when the
 // windows of a launch are too long for shared memory (the loads are sequential 2-byte reads, served by L1).
 template <int G, int K, bool HAS_N, bool DEFAULT_SC, bool SEL_GLOBAL, int THREADS>
@@ -202,37 +239,7 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
     if (!keep_hi) stepB = s;
   }
 
-  // ---- group arg-max: (score, smaller column, smaller lane) -------------------------------
-  const int scA = (int)(int16_t)(best & 0xFFFFu), scB = (int)(int16_t)(best >> 16);
-  unsigned long long keyA = 0ull, keyB = 0ull;
-  if (scA > 0) keyA = ((unsigned long long)scA << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepA - g + 1)) << 8) | (unsigned long long)(31 - g);
-  if (scB > 0) keyB = ((unsigned long long)scB << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepB - g + 1)) << 8) | (unsigned long long)(31 - g);
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
-    const unsigned long long oa = __shfl_xor_sync(0xffffffffu, keyA, o, G);
-    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, keyB, o, G);
-    keyA = oa > keyA ? oa : keyA; keyB = ob > keyB ? ob : keyB;
-  }
-  if (g == 0) {
-    if (tA != 0xFFFFFFFFu) {
-      FwdOut o = {0, 0, 0, 0};
-      if (keyA) {
-        const int lane = 31 - (int)(keyA & 0xFFu);
-        o.score = (int)(keyA >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyA >> 8) & 0xFFFFu));
-        o.i_lo = lane * K + 1; o.i_hi = min(LA, lane * K + K);
-      }
-      out[tA] = o;
-    }
-    if (tB != 0xFFFFFFFFu) {
-      FwdOut o = {0, 0, 0, 0};
-      if (keyB) {
-        const int lane = 31 - (int)(keyB & 0xFFu);
-        o.score = (int)(keyB >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyB >> 8) & 0xFFFFu));
-        o.i_lo = lane * K + 1; o.i_hi = min(LB, lane * K + K);
-      }
-      out[tB] = o;
-    }
-  }
+  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, out);
 }
 
 }  // namespace ubu

@@ -3,6 +3,7 @@
 // Product path: there is NO CPU alignment code in this library and no fallback; every entry point
 // that needs the GPU fails with UBU_SW_ERR_NO_DEVICE / UBU_SW_ERR_CUDA when it is not there.
 #include "sw_fwd16.cuh"
+#include "sw_fwd16s.cuh"
 #include "sw_tb.cuh"
 #include "sw_tbrect.cuh"
 #include "sw_post.cuh"
@@ -70,7 +71,7 @@ struct PinBuf {
 };
 
 constexpr int kAux = 5;
-struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; };   // selectors go to global scratch when they do not fit shared memory
+struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; bool shared_win = false; };   // shared_win: both tasks of every pair sweep the same window   // selectors go to global scratch when they do not fit shared memory
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -96,7 +97,7 @@ struct Slot {
   PinBuf<uint32_t> h_order;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
-  std::vector<uint32_t> tmp_keys;
+  std::vector<uint32_t> tmp_keys, tmp_end;
   // staged batch
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
@@ -134,6 +135,8 @@ int fail_cuda(ubu_sw_handle* h, cudaError_t e, const char* what) {
 }
 #define CU(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda((h), e__, #call); } while (0)
 
+bool env_off(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
+
 int cfg_of_len(int L) {
   for (int c = 0; c < kNumCfgs; ++c) if (L <= kFwdCfgs[c].lmax) return c;
   return -1;
@@ -164,9 +167,50 @@ cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs
   return cudaGetLastError();
 }
 
+#ifndef UBU_FWDS_THREADS
+#define UBU_FWDS_THREADS 32
+#endif
+constexpr int FWDS_THREADS = UBU_FWDS_THREADS;
+int fwds_sel_stride(int wmax, int G) { return ((wmax + 2 * G + 15) / 16) * 16; }
+
+// Shared-window pairs: query profile in shared memory (sw_fwd16s.cuh). Returns cudaErrorInvalidConfiguration when the profile +
+// selectors of a CTA do not fit shared memory; the caller then uses the general kernel.
+template <int G, int K, bool HAS_N, bool DEF>
+cudaError_t launch_fwds_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
+                          const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+  constexpr int GP = FWDS_THREADS / G;
+  const int stride = fwds_sel_stride(L.wmax, G);
+  const size_t smem = FwdsLayout<G, K, HAS_N>::smem_bytes(GP, stride);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidConfiguration;
+  const uint32_t pairs = L.n_slots / 2;
+  const uint32_t grid = (pairs + GP - 1) / GP;
+  const uint32_t* ord = order ? order + L.begin : nullptr;
+  auto kern = sw_fwd16s_kernel<G, K, HAS_N, DEF, FWDS_THREADS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, FWDS_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
                        const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, cudaStream_t st) {
   const bool def = sc.match == 1 && sc.mismatch == -3 && sc.gap_open == 5 && sc.gap_ext == 2;
+  if (L.shared_win) {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
+#define X(i, l, g, k) \
+      case i * 4: e = launch_fwds_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, st); break; \
+      case i * 4 + 1: e = launch_fwds_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, st); break; \
+      case i * 4 + 2: e = launch_fwds_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, st); break; \
+      case i * 4 + 3: e = launch_fwds_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, st); break;
+      UBU_FWD_CFGS(X)
+#undef X
+      default: break;
+    }
+    if (e != cudaErrorInvalidConfiguration) return e;          // does not fit shared memory: general kernel below
+  }
   switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
 #define X(i, l, g, k) \
     case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, gsel, st); \
@@ -254,7 +298,46 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       s.n_slots = (n + 1u) & ~1u;
       s.identity_order = true;
       s.launches.clear();
-      s.launches.push_back(FwdLaunch{c1, false, 0u, s.n_slots, (int)wmax, n});
+      FwdLaunch L{c1, false, 0u, s.n_slots, (int)wmax, n};
+      if (idx && !env_off("UBU_NO_SHARED_WIN")) {             // do the two tasks of every pair share their window?
+        uint32_t diff = 0;
+        for (uint32_t t = 0; t + 1 < n; t += 2) diff |= idx[t] ^ idx[t + 1];
+        L.shared_win = diff == 0;
+        if (!L.shared_win && (uint64_t)wins->count * 3u <= (uint64_t)n * 2u) {
+          // Many reads per window, but not as neighbours: group the reads by window (counting sort, two passes) so that
+          // most pairs share their window and run on the query-profile kernel; the odd read of a window joins the
+          // general launch behind them.
+          const uint32_t nw = wins->count;
+          s.tmp_keys.assign((size_t)2 * nw + 2, 0u);
+          uint32_t* cnt = s.tmp_keys.data(); uint32_t* pos = cnt + nw + 1;
+          for (uint32_t t = 0; t < n; ++t) ++cnt[idx[t]];
+          uint32_t n_pair_slots = 0, n_left = 0;
+          for (uint32_t w = 0; w < nw; ++w) { n_pair_slots += cnt[w] & ~1u; n_left += cnt[w] & 1u; }
+          const uint32_t left_slots = (n_left + 1u) & ~1u;
+          s.n_slots = n_pair_slots + left_slots;
+          if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots, 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
+          uint32_t* order = s.h_order.p;
+          std::vector<uint32_t>& endv = s.tmp_end;           // endv[w]: end of window w's pair slots
+          endv.resize(nw);
+          uint32_t pp = 0, lp = n_pair_slots;
+          for (uint32_t w = 0; w < nw; ++w) {                // pos[w]: next pair slot of window w
+            const uint32_t c = cnt[w];
+            pos[w] = pp; pp += c & ~1u; endv[w] = pp;
+            cnt[w] = (c & 1u) ? lp++ : 0xFFFFFFFFu;          // cnt[w] now = the slot of window w's odd read (general launch)
+          }
+          for (uint32_t t = 0; t < n; ++t) {
+            const uint32_t w = idx[t];
+            if (pos[w] < endv[w]) order[pos[w]++] = t; else order[cnt[w]] = t;
+          }
+          if (n_left & 1u) order[s.n_slots - 1] = 0xFFFFFFFFu;
+          s.launches.clear();
+          if (n_pair_slots) { FwdLaunch A{c1, false, 0u, n_pair_slots, (int)wmax, 0u}; A.shared_win = true; s.launches.push_back(A); }
+          if (left_slots) s.launches.push_back(FwdLaunch{c1, false, n_pair_slots, left_slots, (int)wmax, 0u});
+          s.identity_order = false;
+          return UBU_SW_OK;
+        }
+      }
+      s.launches.push_back(L);
       return UBU_SW_OK;
     }
   }
@@ -331,7 +414,14 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       }
       int wm = 0;
       for (uint32_t k = beg; k < end && k < cnt[b]; ++k) wm = std::max(wm, (int)(s.tmp_keys[lo[k]] & 0xFFFFu));
-      s.launches.push_back(FwdLaunch{cfg, has_n, start[b] + beg, end - beg, wm, 0u});
+      FwdLaunch L{cfg, has_n, start[b] + beg, end - beg, wm, 0u};
+      if (idx && !env_off("UBU_NO_SHARED_WIN")) {            // pairs whose two tasks share a window (mates, reads of one contig)
+        bool sh = true;
+        for (uint32_t k = beg; sh && k + 1 < end; k += 2)
+          if (lo[k] != 0xFFFFFFFFu && lo[k + 1] != 0xFFFFFFFFu && idx[lo[k]] != idx[lo[k + 1]]) sh = false;
+        L.shared_win = sh;
+      }
+      s.launches.push_back(L);
       beg = end;
     }
   }
