@@ -185,7 +185,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step (cfg2 = 1,000,000)")
-    ap.add_argument("--chunk", type=int, default=250_000, help="reads per submit() in the end-to-end leg")
+    ap.add_argument("--chunk", type=int, default=62_500, help="reads per submit() in the end-to-end leg")
+    ap.add_argument("--slots", type=int, default=6, help="pipeline depth (submits in flight) of the end-to-end leg")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the bounded CPU-oracle sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
@@ -235,7 +236,7 @@ def main():
     want_cpu = (rank == 0 and world == 1 and not args.no_cpu)
     w = make_workload(n, rank, keep_codes=want_cpu)
     cells = float(w.cells)
-    al = U.SwAligner(device=local, slots=3)
+    al = U.SwAligner(device=local, slots=args.slots)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     sampler = ClockSampler(local)          # clocks / throttle reasons across the whole measured part (both legs)
@@ -332,15 +333,15 @@ def main():
         fwd_gcups = cells / fwd_s / 1e9
         algo_bytes = (w.reads.packed.nbytes + w.windows.packed.nbytes + n * (4 + 2 + 4 + 4) + w.windows.count * 6 + n * 16)
         roofline = {
-            "bound": "int_alu", "kernel": "sw_fwd16_kernel<G=4,K=19> (forward score pass; 76 bp class)",
+            "bound": "int_alu", "kernel": "sw_fwd16s_kernel<G=4,K=19> (forward score pass, shared-window pairs; 76 bp class)",
             "achieved": fwd_gcups, "peak": peak["roofline_gcups"], "unit": "GCUPS", "frac": fwd_gcups / peak["roofline_gcups"],
             "peak_source": f"bench/peak_int16x2.cu ({peak['source']}): {peak['instr_per_clk_per_sm']:.2f} warp-instr/clk/SM on the "
                            f"4 ALU : 3 VIADD cell mix at {peak['sm_mhz']:.0f} MHz x 148 SMs x 32 lanes x 2 cells / 7 ops",
             "alu_pipe_only_peak": peak.get("alu_only_roofline_gcups"),
             "ops_per_cell": 7, "launch_ms": fwd_s * 1e3, "share_of_step": float(np.mean(fwd_ms) / np.mean(ev_ms)),
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu capture
-            # (profiles/fwd16_r01.txt: 94.57 MB + 6.65 MB); only meaningful for the default 1M-read cfg2 launch
-            "traffic": 101.2e6 if n == 1_000_000 else None, "traffic_unit": "bytes per launch (ncu, profiles/fwd16_r01.txt)",
+            # (profiles/fwd16s_r01.txt: 94.54 MB + 7.42 MB); only meaningful for the default 1M-read cfg2 launch
+            "traffic": 102.0e6 if n == 1_000_000 else None, "traffic_unit": "bytes per launch (ncu, profiles/fwd16s_r01.txt)",
             "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": 6551.4,
                     "frac": algo_bytes / fwd_s / 1e9 / 6551.4, "note": "not the bound: ~2e-3 B/cell"},
         }

@@ -82,7 +82,7 @@ typedef struct {
 typedef struct ubu_sw_handle ubu_sw_handle;
 
 /* Stands in for `new Aligner(reference, numThreads)` (Aligner.java:13-16): one handle per GPU.
- * params == NULL -> SPEC defaults. slots = depth of the H2D/compute/D2H pipeline (1..4; 0 -> 2). */
+ * params == NULL -> SPEC defaults. slots = depth of the H2D/compute/D2H pipeline (1..8; 0 -> 2). */
 int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_handle** out);
 void ubu_sw_destroy(ubu_sw_handle* h);
 

@@ -71,6 +71,7 @@ struct PinBuf {
 };
 
 constexpr int kAux = 5;
+constexpr int kMaxSlots = 8;                          // depth of the H2D / compute / D2H pipeline (ubu_sw_create)
 struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; bool shared_win = false; };   // shared_win: both tasks of every pair sweep the same window   // selectors go to global scratch when they do not fit shared memory
 
 struct Slot {
@@ -115,7 +116,7 @@ struct Slot {
 struct ubu_sw_handle {
   int device = 0, n_slots = 2, sm_count = 148;
   Scoring sc = make_scoring(1, -3, 5, 2);
-  Slot slots[4];
+  Slot slots[kMaxSlots];
   std::string last_error;
   int next_slot = 0;
   // resident reference sequences + scratch of the post-alignment calls (ubu_sw_load_refs / recount / project)
@@ -688,7 +689,7 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
   ubu_sw_params p = params ? *params : ubu_sw_params{1, -3, 5, 2};
   if (!params_ok(p)) return UBU_SW_ERR_ARG;
   if (slots == 0) slots = 2;
-  if (slots < 1 || slots > 4) return UBU_SW_ERR_ARG;
+  if (slots < 1 || slots > kMaxSlots) return UBU_SW_ERR_ARG;
   int ndev = ubu_sw_device_count();
   if (device < 0 || device >= ndev) return UBU_SW_ERR_NO_DEVICE;
   cudaDeviceProp prop;
@@ -716,7 +717,7 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
 void ubu_sw_destroy(ubu_sw_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMaxSlots; ++i) {
     Slot& s = h->slots[i];
     if (s.stream) cudaStreamSynchronize(s.stream);
     s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
