@@ -38,7 +38,8 @@ typedef enum {
   UBU_SW_ERR_TOO_LONG = -4,     /* read longer than UBU_SW_MAX_READ                       */
   UBU_SW_ERR_NO_DEVICE = -5,    /* no CUDA device / not an sm_100 device                  */
   UBU_SW_ERR_BUSY = -6,         /* no free pipeline slot / ticket not pending             */
-  UBU_SW_ERR_NOMEM = -7
+  UBU_SW_ERR_NOMEM = -7,
+  UBU_SW_ERR_CAPACITY = -8      /* an output table / node bound was too small; the required count is written back */
 } ubu_sw_status;
 
 #define UBU_SW_MAX_READ   256u      /* rows handled by the packed 16-bit kernel (all BASELINE configs: 50..250 bp) */

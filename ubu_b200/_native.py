@@ -42,7 +42,14 @@ class Refs(C.Structure):
     ]
 
 
+class KmerParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_uint32), ("min_node_frequency", C.c_uint32)]
+
+
 POST_NULL, POST_MALFORMED, POST_POOL = 1, 2, 4
+ERR_CAPACITY = -8
+KMER_NONE = 0xFFFFFFFF
+KMER_FLAG_MULTI_READS, KMER_FLAG_FILTERED, KMER_FLAG_ROOT = 1, 2, 4
 
 # every symbol include/ubu_sw.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -70,6 +77,17 @@ SYMBOLS = [
     ("ubu_sw_version", C.c_uint, []),
     ("ubu_sw_strerror", C.c_char_p, [C.c_int]),
     ("ubu_sw_last_error", C.c_char_p, [C.c_void_p]),
+    # include/ubu_kmer.h
+    ("ubu_kmer_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("ubu_kmer_destroy", None, [C.c_void_p]),
+    ("ubu_kmer_last_error", C.c_char_p, [C.c_void_p]),
+    ("ubu_kmer_build", C.c_int, [C.c_void_p, C.POINTER(KmerParams), C.POINTER(Seqs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                 C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]),
+    ("ubu_kmer_stage", C.c_int, [C.c_void_p, C.POINTER(KmerParams), C.POINTER(Seqs), C.c_void_p, C.c_size_t]),
+    ("ubu_kmer_run", C.c_int, [C.c_void_p]),
+    ("ubu_kmer_fetch", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]),
+    ("ubu_kmer_last_run_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("ubu_kmer_last_run_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

@@ -677,6 +677,7 @@ const char* ubu_sw_strerror(int status) {
     case UBU_SW_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required)";
     case UBU_SW_ERR_BUSY: return "no free pipeline slot / ticket not pending";
     case UBU_SW_ERR_NOMEM: return "out of host memory";
+    case UBU_SW_ERR_CAPACITY: return "output table / node bound too small";
     default: return "unknown status";
   }
 }
