@@ -12,11 +12,13 @@
 //   insertion order of nodes      atomicMin of the occurrence index (read * max_occ + pos) -> output order = the order the
 //                                                                                            Java inserts into Assembler.nodes
 //   hasMultipleUniqueReads        reads are first put into exact equality classes (a hash table over whole reads with a
-//                                 full compare on every hit); a node keeps the min and the max class of its contributors
-//                                 (two atomicMin): they differ iff two different read strings contributed
+//                                 full compare on every hit), named by their smallest member. The first read that
+//                                 contributes to a node is then its own class, so the node only tracks the LARGEST class
+//                                 (one atomicMin on the complement): it differs from the first read iff two different read
+//                                 strings contributed
 //   toNodes / fromNodes order     the successor (predecessor) of a k-mer is determined by one base, so a node has four
-//                                 to-slots and four from-slots; each keeps the atomicMin of the occurrence that first walks
-//                                 the edge (and the neighbour's slot); sorted by that key they are the Java's array order
+//                                 to-slots and four from-slots; each keeps the 64-bit atomicMin of (occurrence that walks
+//                                 the edge << 32 | neighbour's slot); sorted by that key they are the Java's array order
 // All results are therefore independent of the order in which threads run, and bit-identical to the sequential Java.
 // Passes: clear table -> read classes -> insert (+count/first/class/edges) -> sort nodes by first occurrence (cub radix
 // sort, 32-bit keys) -> rank -> emit (filter flag, root flag, neighbour indices).
@@ -44,15 +46,12 @@ struct __align__(128) NodeSlot {
   unsigned long long k0, k1;
   uint32_t region, state;
   uint32_t count_m1;                 // occurrences - 1
-  uint32_t cls_min;                  // min over the contributing reads' equality classes
-  uint32_t first;                    // min occurrence key
-  uint32_t ncls_min;                 // min over ~class = ~max class: two different classes <=> cls_min != ~ncls_min
-  uint32_t to_first[4];              // by appended base: key of the occurrence that first walked the edge
-  uint32_t from_first[4];            // by the predecessor's first base
-  uint32_t to_slot[4];               // the neighbours' slots (every walker of an edge writes the same value)
-  uint32_t from_slot[4];
+  uint32_t first;                    // min occurrence key; first / max_occ = the first contributing read = its own class
+  uint32_t ncls_min;                 // min over ~class = ~(max class): two different read strings <=> max class != first read
   uint32_t rank;                     // index in the output table
-  uint32_t pad[5];
+  unsigned long long to[4];          // by appended base: (key of the occurrence that first walked the edge) << 32 | successor's slot
+  unsigned long long from[4];        // by the predecessor's first base: key << 32 | predecessor's slot
+  uint32_t pad[6];
 };
 static_assert(sizeof(NodeSlot) == 128, "one node = one 128-byte line");
 
@@ -134,20 +133,28 @@ __global__ void kmer_read_class_kernel(DevSeqs reads, const uint32_t* __restrict
     for (int c = 0; 16 * c < L; ++c) { uint32_t w = load16n(m, 16 * c); const int rem = L - 16 * c; if (rem < 16) w &= (1u << rem) - 1u; any |= w; }
     if (any) { cls[r] = NONE; atomicAdd(&ctr[2], 1u); return; }
   }
-  unsigned long long h = 0x51ED270B1ull + (unsigned long long)L;
+  // A class = (region, read string): its members contribute to the same nodes. The table slot ends up holding the
+  // smallest member; cls[r] is the slot for now and is resolved to that member by kmer_read_class_resolve_kernel.
+  const uint32_t reg = region ? region[r] : 0u;
+  unsigned long long h = 0x51ED270B1ull + (unsigned long long)L + ((unsigned long long)reg << 20);
   for (int c = 0; 16 * c < L; ++c) h = mix64(h ^ (unsigned long long)read_chunk(q, L, c));
   uint32_t s = (uint32_t)h & rmask;
   for (;;) {
     const uint32_t old = atomicCAS(&rtab[s], NONE, r);
-    if (old == NONE) { cls[r] = r; return; }
-    bool same = reads.len[old] == L;
+    if (old == NONE) { cls[r] = s; return; }
+    bool same = reads.len[old] == L && (region ? region[old] : 0u) == reg;
     if (same) {
       const uint8_t* o = reads.packed + reads.off[old];
       for (int c = 0; same && 16 * c < L; ++c) same = read_chunk(q, L, c) == read_chunk(o, L, c);
     }
-    if (same) { cls[r] = old; return; }
+    if (same) { atomicMin(&rtab[s], r); cls[r] = s; return; }      // any member serves as the one to compare with
     s = (s + 1u) & rmask;
   }
+}
+
+__global__ void kmer_read_class_resolve_kernel(const uint32_t* __restrict__ rtab, uint32_t n, uint32_t* __restrict__ cls) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n && cls[r] != NONE) cls[r] = rtab[cls[r]];
 }
 
 // ---- pass 2: the hash-table kernel. addToGraph's loop body (Assembler.java:456-472): find-or-create the node, count it, note
@@ -201,13 +208,12 @@ kmer_insert_kernel(DevSeqs reads, const uint32_t* __restrict__ region, const uin
   const uint32_t key = (uint32_t)occ;                                       // ordered like (read, position)
   atomicAdd(&p->count_m1, 1u);
   atomicMin(&p->first, key);
-  atomicMin(&p->cls_min, c); atomicMin(&p->ncls_min, ~c);                   // Node.addReadSequence, Node.java:78-90
+  atomicMin(&p->ncls_min, ~c);                                              // Node.addReadSequence, Node.java:78-90
   if (i > 0u) {                                                             // prev.addToNode(node), Node.java:118-130
     if (prev == NONE) { atomicOr(&ctr[1], 1u); return; }
     const uint32_t b_next = base2(q, i + (uint32_t)k - 1u), b_prev = base2(q, i - 1u);
-    NodeSlot* pp = tab + prev;
-    atomicMin(&pp->to_first[b_next], key); pp->to_slot[b_next] = s;         // the first walk of an edge fixes its place;
-    atomicMin(&p->from_first[b_prev], key); p->from_slot[b_prev] = prev;    // every walker writes the same neighbour slot
+    atomicMin(&tab[prev].to[b_next], ((unsigned long long)key << 32) | (unsigned long long)s);      // the first walk of an edge
+    atomicMin(&p->from[b_prev], ((unsigned long long)key << 32) | (unsigned long long)prev);        // fixes its place in the list
   }
 }
 
@@ -222,8 +228,11 @@ __global__ void kmer_rank_kernel(NodeSlot* __restrict__ tab, const uint32_t* __r
   if (j < n) tab[sorted_slot[j]].rank = j;
 }
 
-__device__ __forceinline__ bool slot_filtered(const NodeSlot* p, uint32_t min_freq) {   // Assembler.java:204-210
-  return p->count_m1 + 1u < min_freq || p->cls_min == ~p->ncls_min;
+__device__ __forceinline__ bool slot_multi(const NodeSlot* p, uint32_t max_occ) {        // Node.hasMultipleUniqueReads
+  return ~p->ncls_min != p->first / max_occ;
+}
+__device__ __forceinline__ bool slot_filtered(const NodeSlot* p, uint32_t min_freq, uint32_t max_occ) {   // Assembler.java:204-210
+  return p->count_m1 + 1u < min_freq || !slot_multi(p, max_occ);
 }
 
 // ---- pass 5: one thread per node, in output order --------------------------------------------------------------------------
@@ -235,19 +244,20 @@ __global__ void kmer_emit_kernel(const NodeSlot* __restrict__ tab, const uint32_
   ubu_kmer_node o;
   o.kmer[0] = p->k0; o.kmer[1] = p->k1; o.region = p->region; o.count = p->count_m1 + 1u;
   o.first_read = p->first / max_occ; o.first_pos = (uint16_t)(p->first % max_occ);
-  const bool filtered = slot_filtered(p, min_freq);
-  uint32_t flags = (p->cls_min != ~p->ncls_min ? UBU_KMER_FLAG_MULTI_READS : 0u) | (filtered ? UBU_KMER_FLAG_FILTERED : 0u);
+  const bool filtered = slot_filtered(p, min_freq, max_occ);
+  uint32_t flags = (slot_multi(p, max_occ) ? UBU_KMER_FLAG_MULTI_READS : 0u) | (filtered ? UBU_KMER_FLAG_FILTERED : 0u);
   uint32_t tkey[4], fkey[4], tnode[4], fnode[4];
   bool live_pred = false;
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    tkey[b] = p->to_first[b]; tnode[b] = NONE;
-    if (tkey[b] != NONE) tnode[b] = tab[p->to_slot[b]].rank;
-    fkey[b] = p->from_first[b]; fnode[b] = NONE;
+    const unsigned long long t = p->to[b], f = p->from[b];
+    tkey[b] = (uint32_t)(t >> 32); tnode[b] = NONE;
+    if (tkey[b] != NONE) tnode[b] = tab[(uint32_t)t].rank;
+    fkey[b] = (uint32_t)(f >> 32); fnode[b] = NONE;
     if (fkey[b] != NONE) {
-      const NodeSlot* f = tab + p->from_slot[b];
-      fnode[b] = f->rank;
-      if (!slot_filtered(f, min_freq)) live_pred = true;
+      const NodeSlot* fp = tab + (uint32_t)f;
+      fnode[b] = fp->rank;
+      if (!slot_filtered(fp, min_freq, max_occ)) live_pred = true;
     }
   }
   if (!filtered && !live_pred) flags |= UBU_KMER_FLAG_ROOT;                 // Assembler.java:270-276 after the filter
@@ -416,6 +426,8 @@ int ubu_kmer_run(ubu_kmer_handle* h) {
   const uint32_t* region = h->has_region ? h->d_region.p : nullptr;
   if (n) {
     kmer_read_class_kernel<<<(n + 127) / 128, 128, 0, st>>>(reads, region, n, h->d_rtab.p, h->rmask, h->d_cls.p, h->d_ctr.p);
+    KCU(h, cudaGetLastError()); ++h->launches;
+    kmer_read_class_resolve_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_rtab.p, n, h->d_cls.p);
     KCU(h, cudaGetLastError()); ++h->launches;
   }
   KCU(h, cudaEventRecord(h->ev[1], st));
