@@ -64,3 +64,37 @@ JNIEXPORT jlong JNICALL Java_edu_unc_bioinf_ubu_assembly_GpuAligner_alignBatch(
   if (rc) { throw_status(env, h, rc); return -1; }
   return (jlong)used;
 }
+
+/* ---- k-mer graph build (include/ubu_kmer.h), Java side: integration/jni/GpuKmerGraph.java. UNTESTED like the rest of this file. ---- */
+#include "ubu_kmer.h"
+
+JNIEXPORT jlong JNICALL Java_edu_unc_bioinf_ubu_assembly_GpuKmerGraph_create(JNIEnv* env, jclass cls, jint device) {
+  ubu_kmer_handle* h = NULL;
+  int rc = ubu_kmer_create(device, &h);
+  if (rc) { throw_status(env, NULL, rc); return 0; }
+  return (jlong)(intptr_t)h;
+}
+
+JNIEXPORT void JNICALL Java_edu_unc_bioinf_ubu_assembly_GpuKmerGraph_destroy(JNIEnv* env, jclass cls, jlong handle) {
+  ubu_kmer_destroy((ubu_kmer_handle*)(intptr_t)handle);
+}
+
+JNIEXPORT jlong JNICALL Java_edu_unc_bioinf_ubu_assembly_GpuKmerGraph_build(JNIEnv* env, jclass cls, jlong handle, jint kmerSize,
+    jint minNodeFrequency, jobject rPacked, jobject rOff, jobject rLen, jobject rNmask, jobject rNmaskOff, jint nReads,
+    jobject readRegion, jlong maxNodes, jobject nodes) {
+  ubu_kmer_handle* h = (ubu_kmer_handle*)(intptr_t)handle;
+  ubu_sw_seqs reads;
+  fill(env, &reads, rPacked, rOff, rLen, rNmask, rNmaskOff, nReads);
+  ubu_kmer_params p = {(uint32_t)kmerSize, (uint32_t)minNodeFrequency};
+  const uint32_t* region = readRegion ? (const uint32_t*)(*env)->GetDirectBufferAddress(env, readRegion) : NULL;
+  size_t n_nodes = 0;
+  int rc = ubu_kmer_build(h, &p, &reads, region, (size_t)maxNodes, (ubu_kmer_node*)(*env)->GetDirectBufferAddress(env, nodes),
+                          (size_t)(*env)->GetDirectBufferCapacity(env, nodes) / sizeof(ubu_kmer_node), &n_nodes, NULL);
+  if (rc) {
+    char msg[320];
+    snprintf(msg, sizeof msg, "ubu_kmer failed: %s (%s); nodes needed: %zu", ubu_sw_strerror(rc), ubu_kmer_last_error(h), n_nodes);
+    (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), msg);
+    return 0;
+  }
+  return (jlong)n_nodes;
+}

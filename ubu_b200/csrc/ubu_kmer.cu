@@ -82,11 +82,15 @@ __device__ __forceinline__ uint32_t ld_state(const NodeSlot* s) { return *reinte
 // The first 32 bytes of a slot (key, region, state) are fetched in one round trip. A full slot's key never changes, so a
 // match read together with state == FULL is final; a MISMATCH may be a key read before its owner published it, and is
 // confirmed by a second read that is ordered after the FULL state.
+// `overflow` (set by whoever finds the node bound exceeded) is polled every 64 probes: once the batch is known to need a
+// bigger table nobody keeps walking a nearly full one.
 __device__ __forceinline__ uint32_t find_or_insert(NodeSlot* __restrict__ tab, unsigned long long mask, unsigned long long k0,
-                                                   unsigned long long k1, uint32_t region, bool& created) {
+                                                   unsigned long long k1, uint32_t region, bool& created,
+                                                   const unsigned int* overflow) {
   created = false;
   unsigned long long s = node_hash(k0, k1, region) & mask;
   for (unsigned long long probes = 0; probes <= mask; ++probes, s = (s + 1ull) & mask) {
+    if ((probes & 63ull) == 63ull && *reinterpret_cast<const volatile unsigned int*>(overflow)) return NONE;
     NodeSlot* p = tab + s;
     const uint4 a = __ldcv(reinterpret_cast<const uint4*>(p));          // k0, k1
     const uint2 b = __ldcv(reinterpret_cast<const uint2*>(p) + 2);      // region, state
@@ -180,6 +184,7 @@ kmer_insert_kernel(DevSeqs reads, const uint32_t* __restrict__ region, const uin
   // lane 0 is needed only as the predecessor of lane 1's occurrence (same read, so lane 1 is at a position > 0)
   const bool owner = lane != 0u;
   if (!owner) valid = valid && i + 1u < max_occ;
+  if (*reinterpret_cast<const volatile unsigned int*>(ctr + 1)) valid = false;          // the run already failed (node bound exceeded)
   const uint8_t* q = valid ? reads.packed + reads.off[r] : nullptr;
   const uint32_t reg = (valid && region) ? region[r] : 0u;
   uint32_t s = NONE;
@@ -187,7 +192,7 @@ kmer_insert_kernel(DevSeqs reads, const uint32_t* __restrict__ region, const uin
   if (valid) {
     unsigned long long k0, k1;
     load_kmer(q, (int)i, k, k0, k1);
-    s = find_or_insert(tab, mask, k0, k1, reg, created);
+    s = find_or_insert(tab, mask, k0, k1, reg, created, ctr + 1);
   }
   const uint32_t prev = __shfl_up_sync(0xffffffffu, s, 1);                 // slot of occurrence occ - 1 (same read when i > 0)
   // new nodes are appended to the node list with one counter update per warp
