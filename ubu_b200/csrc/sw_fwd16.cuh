@@ -45,10 +45,12 @@ namespace ubu {
 #define UBU_FWD_UNROLL 2
 #endif
 // Group arg-max of the forward sweep and the FwdOut records of the pair: candidates are ordered by
-// (score, smaller column, smaller lane), which is SPEC.md section 4 at lane granularity.
+// (score, smaller column, smaller lane), which is SPEC.md section 4 at lane granularity. A path of score S ending in row i
+// holds at most i matches, so the end row is at least ceil(S / match): rows of the winning lane below that are dropped
+// from the candidate range (a narrower traceback band).
 template <int G, int K>
 __device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA, int stepB, int g, uint32_t tA, uint32_t tB, int LA, int LB,
-                                                       FwdOut* __restrict__ out) {
+                                                       int match, FwdOut* __restrict__ out) {
   const int scA = (int)(int16_t)(best & 0xFFFFu), scB = (int)(int16_t)(best >> 16);
   unsigned long long keyA = 0ull, keyB = 0ull;
   if (scA > 0) keyA = ((unsigned long long)scA << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepA - g + 1)) << 8) | (unsigned long long)(31 - g);
@@ -65,7 +67,7 @@ __device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA,
       if (keyA) {
         const int lane = 31 - (int)(keyA & 0xFFu);
         o.score = (int)(keyA >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyA >> 8) & 0xFFFFu));
-        o.i_lo = lane * K + 1; o.i_hi = min(LA, lane * K + K);
+        o.i_lo = max(lane * K + 1, (o.score + match - 1) / match); o.i_hi = min(LA, lane * K + K);
       }
       out[tA] = o;
     }
@@ -74,7 +76,7 @@ __device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA,
       if (keyB) {
         const int lane = 31 - (int)(keyB & 0xFFu);
         o.score = (int)(keyB >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyB >> 8) & 0xFFFFu));
-        o.i_lo = lane * K + 1; o.i_hi = min(LB, lane * K + K);
+        o.i_lo = max(lane * K + 1, (o.score + match - 1) / match); o.i_hi = min(LB, lane * K + K);
       }
       out[tB] = o;
     }
@@ -239,7 +241,7 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
     if (!keep_hi) stepB = s;
   }
 
-  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, out);
+  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc.match, out);
 }
 
 }  // namespace ubu

@@ -219,7 +219,7 @@ sw_fwd16s_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_i
     if (!keep_hi) stepB = s;
   }
 
-  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, out);
+  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc.match, out);
 }
 
 }  // namespace ubu
