@@ -65,8 +65,11 @@ def main():
             "ms": {"total": float(m[0]), "clear_and_read_classes": float(m[1]), "insert_and_edges": float(m[2]), "order_and_emit": float(m[3])},
             "config": {"reads": int(codes.shape[0]), "read_len": a.read_len, "regions": a.regions, "shuffled": bool(a.shuffle), "k": a.k, "occurrences": occ,
                        "nodes": int(n_nodes), "table_bytes": table_bytes, "launches": launches},
-            # one 128-byte node line read and written per occurrence by the insert kernel, one more line touched per edge walk
-            "hbm_model": {"bytes_per_occurrence": 3 * 128, "achieved_gbs": occ * 3 * 128 / (m[2] * 1e-3) / 1e9}}
+            # algorithmic traffic of the hash-table kernel: the node's 128-byte line comes in from HBM and goes back once per
+            # occurrence (the table is far larger than L2 and concurrent warps work on distant reads); peak = MEASURED_PEAKS hbm
+            "roofline": {"bound": "hbm", "kernel": "kmer_insert_kernel", "bytes_per_occurrence": 256,
+                         "achieved": occ * 256 / (m[2] * 1e-3) / 1e9, "peak": 6551.4, "unit": "GB/s",
+                         "frac": occ * 256 / (m[2] * 1e-3) / 1e9 / 6551.4}}
     if a.cpu_regions:
         import kmer_oracle as KO
 
