@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -116,6 +117,52 @@ __device__ __forceinline__ uint32_t find_or_insert(NodeSlot* __restrict__ tab, u
   return NONE;
 }
 
+// 128-bit compare-and-swap on a 16-byte aligned key (atom.cas.b128, sm_90+): returns the previous value.
+__device__ __forceinline__ void cas128(void* addr, unsigned long long cmp_lo, unsigned long long cmp_hi, unsigned long long new_lo,
+                                       unsigned long long new_hi, unsigned long long& old_lo, unsigned long long& old_hi) {
+  asm volatile("{\n\t"
+               ".reg .b128 c, n, o;\n\t"
+               "mov.b128 c, {%2, %3};\n\t"
+               "mov.b128 n, {%4, %5};\n\t"
+               "atom.global.cas.b128 o, [%6], c, n;\n\t"
+               "mov.b128 {%0, %1}, o;\n\t"
+               "}"
+               : "=l"(old_lo), "=l"(old_hi) : "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi), "l"(addr) : "memory");
+}
+
+// Lock-free find-or-create for k <= 63 (a valid k-mer then never equals the all-ones EMPTY key, and its high word is never
+// all ones). A 128-bit CAS installs the k-mer in an empty slot; a slot whose key matches belongs to the first region that
+// claims it with a 32-bit CAS on the region word (the same k-mer of another region moves on to the next slot). No lock, no
+// fence, no spinning: key and region are each written by exactly one atomic and never change afterwards.
+// The common case (the node exists) costs one round trip of plain loads and no atomic: a key read whose two 64-bit words
+// are both different from all-ones is a complete, final key, whatever the hardware does about 128-bit tearing; any read with
+// an all-ones word (empty, possibly mid-install, or a k-mer starting with 32 G) is settled by the CAS instead.
+__device__ __forceinline__ uint32_t find_or_insert_lockfree(NodeSlot* __restrict__ tab, unsigned long long mask, unsigned long long k0,
+                                                            unsigned long long k1, uint32_t region, bool& created,
+                                                            const unsigned int* overflow) {
+  created = false;
+  unsigned long long s = node_hash(k0, k1, region) & mask;
+  for (unsigned long long probes = 0; probes <= mask; ++probes, s = (s + 1ull) & mask) {
+    if ((probes & 63ull) == 63ull && *reinterpret_cast<const volatile unsigned int*>(overflow)) return NONE;
+    NodeSlot* p = tab + s;
+    const ulonglong2 a = __ldcv(reinterpret_cast<const ulonglong2*>(p));
+    uint32_t r = __ldcv(&p->region);
+    unsigned long long o0 = a.x, o1 = a.y;
+    if (o0 == ~0ull || o1 == ~0ull) {                                     // not a settled key: let the CAS decide
+      cas128(p, ~0ull, ~0ull, k0, k1, o0, o1);
+      if ((o0 & o1) == ~0ull) { o0 = k0; o1 = k1; r = NONE; }             // installed just now: nobody has claimed it yet ...
+      else r = __ldcv(&p->region);                                        // ... unless the CAS below says otherwise
+    }
+    if (o0 != k0 || o1 != k1) continue;                                   // another k-mer lives here
+    if (r == NONE) {
+      r = atomicCAS(&p->region, NONE, region);
+      if (r == NONE) { created = true; return (uint32_t)s; }
+    }
+    if (r == region) return (uint32_t)s;
+  }
+  return NONE;
+}
+
 // ---- pass 1: exact equality classes of the reads (Node.addReadSequence compares read STRINGS, Node.java:78-90) -----------
 __device__ __forceinline__ uint32_t read_chunk(const uint8_t* __restrict__ seq, int L, int c) {   // 16 bases, tail masked
   const int rem = L - 16 * c;
@@ -167,17 +214,22 @@ __global__ void kmer_read_class_resolve_kernel(const uint32_t* __restrict__ rtab
 // the occurrence before them, so that every lane gets its predecessor's slot from the lane below by shuffle and all 32 lookups
 // run side by side (no lane does a second, serialised lookup). After the lookup everything is a fire-and-forget reduction.
 constexpr int KMER_OCC_PER_WARP = 31;
+constexpr unsigned long long KMER_PERM_MUL = 1000003ull;       // prime, larger than any permutation block
 
+template <bool LOCKFREE>
 __global__ void __launch_bounds__(256)
 kmer_insert_kernel(DevSeqs reads, const uint32_t* __restrict__ region, const uint32_t* __restrict__ cls, uint32_t n_reads,
                    uint32_t max_occ, int k, NodeSlot* __restrict__ tab, unsigned long long mask, uint32_t* __restrict__ node_list,
-                   unsigned int* __restrict__ ctr, uint32_t max_nodes, unsigned long long n_warps, unsigned long long warp_mul) {
-  // Warps that run at the same time take occurrences that are far apart in the batch (a multiplicative permutation of the
-  // warp index, warp_mul coprime to n_warps): neighbouring reads of a region cover the same k-mers, and spreading them in
-  // time keeps their reductions from queueing on the same L2 lines (+20 % measured against batch order).
+                   unsigned int* __restrict__ ctr, uint32_t max_nodes, unsigned long long n_warps, unsigned long long perm_warps) {
+  // Warps that run at the same time take occurrences that are far apart (a multiplicative permutation of the warp index
+  // inside blocks of KMER_PERM_WARPS warps): neighbouring reads of a region cover the same k-mers, and spreading them in
+  // time keeps their reductions from queueing on the same L2 lines; keeping the permutation inside a block of ~4M
+  // occurrences keeps that block's nodes L2-resident while it is being worked on.
   const unsigned long long hw_warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (hw_warp >= n_warps) return;
-  const unsigned long long gwarp = (hw_warp * warp_mul) % n_warps;
+  const unsigned long long blk = hw_warp / perm_warps, base = blk * perm_warps;
+  const unsigned long long span = n_warps - base < perm_warps ? n_warps - base : perm_warps;
+  const unsigned long long gwarp = base + ((hw_warp - base) * KMER_PERM_MUL) % span;      // KMER_PERM_MUL is prime and > span
   const uint32_t lane = threadIdx.x & 31u;
   const long long occ = (long long)gwarp * KMER_OCC_PER_WARP + (long long)lane - 1;     // lane 0: the occurrence before the warp's
   uint32_t r = 0u, i = 0u, c = NONE;
@@ -197,7 +249,7 @@ kmer_insert_kernel(DevSeqs reads, const uint32_t* __restrict__ region, const uin
   if (valid) {
     unsigned long long k0, k1;
     load_kmer(q, (int)i, k, k0, k1);
-    s = find_or_insert(tab, mask, k0, k1, reg, created, ctr + 1);
+    s = LOCKFREE ? find_or_insert_lockfree(tab, mask, k0, k1, reg, created, ctr + 1) : find_or_insert(tab, mask, k0, k1, reg, created, ctr + 1);
   }
   const uint32_t prev = __shfl_up_sync(0xffffffffu, s, 1);                 // slot of occurrence occ - 1 (same read when i > 0)
   // new nodes are appended to the node list with one counter update per warp
@@ -445,12 +497,15 @@ int ubu_kmer_run(ubu_kmer_handle* h) {
   if (total_occ) {
     const unsigned long long warps = (total_occ + KMER_OCC_PER_WARP - 1) / KMER_OCC_PER_WARP;
     const unsigned int grid = (unsigned int)((warps * 32ull + 255ull) / 256ull);
-    unsigned long long mul = 1000003ull % warps;
-    auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { const unsigned long long t = a % b; a = b; b = t; } return a; };
-    while (mul > 1ull && gcd(mul, warps) != 1ull) ++mul;
-    if (mul < 1ull || warps < 4ull) mul = 1ull;
-    kmer_insert_kernel<<<grid, 256, 0, st>>>(reads, region, h->d_cls.p, n, h->max_occ, k, h->d_tab.p, h->mask, h->d_list.p, h->d_ctr.p,
-                                            h->max_nodes, warps, mul);
+    unsigned long long perm = 131072ull;                                      // warps per permutation block (~4M occurrences)
+    if (const char* e = getenv("UBU_KMER_PERM_WARPS")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v >= 1ull && v < KMER_PERM_MUL) perm = v; }
+    // k <= 63: lock-free slots (a k-mer never equals the empty key); k = 64 uses every bit pattern, so it keeps the state word
+    if (k <= 63 && !getenv("UBU_KMER_LOCKED"))
+      kmer_insert_kernel<true><<<grid, 256, 0, st>>>(reads, region, h->d_cls.p, n, h->max_occ, k, h->d_tab.p, h->mask, h->d_list.p,
+                                                    h->d_ctr.p, h->max_nodes, warps, perm);
+    else
+      kmer_insert_kernel<false><<<grid, 256, 0, st>>>(reads, region, h->d_cls.p, n, h->max_occ, k, h->d_tab.p, h->mask, h->d_list.p,
+                                                     h->d_ctr.p, h->max_nodes, warps, perm);
     KCU(h, cudaGetLastError()); ++h->launches;
   }
   KCU(h, cudaEventRecord(h->ev[2], st));
