@@ -145,6 +145,43 @@ def cpu_arm(w, n_sample: int, threads: int, repeats: int = 1):
     return cells / best / 1e9, n / best, best, res
 
 
+def packing_leg(w, threads: int):
+    """Host-side 2-bit packing of the step's text (reads + windows) with ubu_sw_pack_batch on all host cores: not part of the
+    GCUPS figures (packing is reported separately), but it feeds the same pipeline."""
+    import ctypes as C
+
+    from ubu_b200 import _native as N
+
+    chars = np.frombuffer(b"ACTG", dtype=np.uint8)
+    out = {}
+    total_s, total_bytes = 0.0, 0
+    for name, codes in (("reads", w.read_codes), ("windows", w.window_codes)):
+        n, L = codes.shape
+        text = chars[codes].reshape(-1)
+        toff = (np.arange(n, dtype=np.uint64) * np.uint64(L))
+        lens = np.full(n, L, dtype=np.uint16)
+        pb, nb = (L + 3) // 4, (L + 7) // 8
+        off = (np.arange(n, dtype=np.int64) * pb).astype(np.uint32); noff = (np.arange(n, dtype=np.int64) * nb).astype(np.uint32)
+        packed = np.zeros(n * pb, dtype=np.uint8); nmask = np.zeros(n * nb, dtype=np.uint8)
+        cnt = C.c_uint32(0)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rc = N.lib().ubu_sw_pack_batch(text.ctypes.data, toff.ctypes.data, lens.ctypes.data, n, packed.ctypes.data, off.ctypes.data,
+                                           nmask.ctypes.data, noff.ctypes.data, threads, C.byref(cnt))
+            dt = time.perf_counter() - t0
+            assert rc == 0 and cnt.value == 0
+            best = dt if best is None else min(best, dt)
+        ref = w.reads if name == "reads" else w.windows
+        assert np.array_equal(packed, ref.packed[: packed.size]), "batch packer disagrees with the workload's packing"
+        out[name + "_ms"] = best * 1e3
+        total_s += best; total_bytes += text.size
+    out.update({"ms_per_step": total_s * 1e3, "text_gb_per_s": total_bytes / total_s / 1e9, "reads_per_s": w.n_tasks / total_s,
+                "threads": threads, "how": "ubu_sw_pack_batch (AVX2: 32 characters per step per thread) over the step's ASCII reads and windows, "
+                "best of 3, output buffers preallocated; not included in value / e2e"})
+    return out
+
+
 def run_reference_arm(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
@@ -371,6 +408,8 @@ def main():
                                 "sample": f"first {ns} of the {n} reads of this run's workload, {dt:.2f} s wall; SPEC oracle "
                                           "(oracle/sw_oracle.c, full-matrix 32-bit + traceback); NOT a reference Java aligner (none exists)",
                                 "gpu_results_match_on_sample": bool(agree)}
+    if want_cpu:
+        line["packing"] = packing_leg(w, os.cpu_count() or 1)
     if rank == 0:
         print(json.dumps(line))
     al.close()

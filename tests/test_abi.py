@@ -102,3 +102,28 @@ def test_seqset_roundtrip_and_uniform_packer():
     s = U.pack_codes(ragged)
     for k, c in enumerate(ragged):
         assert np.array_equal(s.codes(k), c)
+
+
+def test_batch_packer_matches_the_numpy_packer():
+    """ubu_sw_pack_batch (8 characters per step, all cores) against the numpy packer: ragged lengths, both cases, N and other
+    non-ACGT bytes at every position of the 8-character groups, empty sequences."""
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ACGTacgtNnRY-*", dtype=np.uint8)
+    p = np.array([.2, .2, .2, .2, .04, .04, .04, .04, .01, .005, .005, .005, .005, .01]); p = p / p.sum()
+    texts = [alphabet[rng.choice(len(alphabet), size=int(n), p=p)].tobytes() for n in
+             list(rng.integers(0, 300, size=4000)) + [0, 1, 7, 8, 9, 15, 16, 17, 255, 256, 65535]]
+    texts += [b"ACGT" * 19, b"acgtacgt", b"NNNNNNNNN", b"ACGTACGN", b"NCGTACGT"]
+    lens = np.array([len(t) for t in texts], dtype=np.uint16)
+    off = np.zeros(len(texts), dtype=np.uint64); off[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
+    buf = np.frombuffer(b"".join(texts), dtype=np.uint8)
+    ref = U.pack_texts(texts)
+    for threads in (1, 0, 3):
+        got = U.pack_text_batch(buf, off, lens, threads=threads)
+        assert np.array_equal(got.len, ref.len) and np.array_equal(got.off, ref.off)
+        assert np.array_equal(got.packed, ref.packed[: got.packed.size])
+        assert got.nmask is not None and np.array_equal(got.nmask, ref.nmask[: got.nmask.size]) and np.array_equal(got.nmask_off, ref.nmask_off)
+    clean = [t for t in texts if not (set(t) - set(b"ACGTacgt"))]
+    lens = np.array([len(t) for t in clean], dtype=np.uint16)
+    off = np.zeros(len(clean), dtype=np.uint64); off[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
+    got = U.pack_text_batch(np.frombuffer(b"".join(clean), dtype=np.uint8), off, lens)
+    assert got.nmask is None and np.array_equal(got.packed, U.pack_texts(clean).packed[: got.packed.size])

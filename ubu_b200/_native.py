@@ -71,6 +71,8 @@ SYMBOLS = [
     ("ubu_sw_host_alloc", C.c_void_p, [C.c_size_t]),
     ("ubu_sw_host_free", None, [C.c_void_p]),
     ("ubu_sw_pack", None, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    ("ubu_sw_pack_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_uint32)]),
     ("ubu_sw_revcomp", None, [C.c_char_p, C.c_size_t, C.c_char_p]),
     ("ubu_sw_cigar_string", C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]),
     ("ubu_sw_device_count", C.c_int, []),

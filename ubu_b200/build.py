@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 UNITS = {
     "ubu_sw.cu": ["sw_common.cuh", "sw_fwd16.cuh", "sw_fwd16s.cuh", "sw_tb.cuh", "sw_tbrect.cuh", "sw_post.cuh"],
     "ubu_kmer.cu": ["sw_common.cuh"],
+    "ubu_pack.cu": [],
 }
 HEADERS = [os.path.join(ROOT, "include", f) for f in ("ubu_sw.h", "ubu_kmer.h")]
 OBJ_DIR = os.path.join(ROOT, "build", "obj")

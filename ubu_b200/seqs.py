@@ -148,6 +148,36 @@ def pack_uniform(codes: np.ndarray) -> SeqSet:
     return SeqSet(np.ascontiguousarray(packed), off, np.full(n, L, dtype=np.uint16), None, None)
 
 
+def pack_text_batch(text: np.ndarray, text_off: np.ndarray, lens: np.ndarray, threads: int = 0, with_nmask: bool = True) -> SeqSet:
+    """ubu_sw_pack_batch: packs a whole batch of ASCII sequences on the host's cores (32 or 8 characters per step per thread).
+    text: uint8 buffer; sequence k = text[text_off[k] : text_off[k] + lens[k]]. The N plane is dropped when no sequence has one."""
+    import ctypes as C
+
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    text_off = np.ascontiguousarray(text_off, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.uint16)
+    n = int(lens.shape[0])
+    pb = (lens.astype(np.int64) + 3) // 4
+    nb = (lens.astype(np.int64) + 7) // 8
+    off = np.zeros(n, dtype=np.int64); noff = np.zeros(n, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum(pb)[:-1]; noff[1:] = np.cumsum(nb)[:-1]
+    if n and off[-1] + pb[-1] >= 2 ** 32:
+        raise ValueError("batch larger than 4 GiB packed; split it")
+    packed = np.zeros(int(pb.sum()), dtype=np.uint8)
+    nmask = np.zeros(int(nb.sum()), dtype=np.uint8) if with_nmask else None
+    off32, noff32 = off.astype(np.uint32), noff.astype(np.uint32)
+    cnt = C.c_uint32(0)
+    rc = N.lib().ubu_sw_pack_batch(text.ctypes.data, text_off.ctypes.data, lens.ctypes.data, n, packed.ctypes.data, off32.ctypes.data,
+                                   nmask.ctypes.data if nmask is not None else None, noff32.ctypes.data if nmask is not None else None,
+                                   threads, C.byref(cnt))
+    if rc != N.OK:
+        raise N.UbuSwError(rc)
+    if nmask is not None and cnt.value == 0:
+        nmask = None
+    return SeqSet(packed, off32, lens, nmask, noff32 if nmask is not None else None)
+
+
 def reverse_complement(text: str) -> str:
     """ReverseComplementor.java:38-62 through the library helper (A<->T, C<->G, others unchanged)."""
     import ctypes as C
