@@ -214,3 +214,38 @@ def test_device_graph_full_size_properties():
             assert (K.kmer_string(nd, k), int(nd["count"]), int(nd["first_read"]) - int(sel[0]), int(nd["first_pos"]),
                     bool(nd["flags"] & N.KMER_FLAG_FILTERED), bool(nd["flags"] & N.KMER_FLAG_ROOT)) == \
                    (r["kmer"], r["count"], r["first_read"], r["first_pos"], r["filtered"], r["root"])
+
+
+# ------------------------------------------------------------------ CPU: the host-side contig walk over a node table ----------------
+def table_from_oracle_rows(rows, k):
+    """The oracle's rows in the device table's format (what ubu_kmer_build returns), so that the host-side walk can be tested
+    without a GPU."""
+    index = {(r["region"], r["kmer"]): j for j, r in enumerate(rows)}
+    code = {"A": 0, "C": 1, "T": 2, "G": 3}
+    t = np.zeros(len(rows), dtype=K.NODE_DTYPE)
+    t["to_node"] = N.KMER_NONE; t["from_node"] = N.KMER_NONE
+    for j, r in enumerate(rows):
+        v = sum(code[ch] << (2 * p) for p, ch in enumerate(r["kmer"]))
+        t[j]["kmer"] = (v & ((1 << 64) - 1), v >> 64)
+        t[j]["region"], t[j]["count"], t[j]["first_read"], t[j]["first_pos"] = r["region"], r["count"], r["first_read"], r["first_pos"]
+        t[j]["flags"] = (N.KMER_FLAG_MULTI_READS if r["multi"] else 0) | (N.KMER_FLAG_FILTERED if r["filtered"] else 0) | \
+                        (N.KMER_FLAG_ROOT if r["root"] else 0)
+        for q, key in enumerate(r["to"]):
+            t[j]["to_node"][q] = index[key]
+        for q, key in enumerate(r["from"]):
+            t[j]["from_node"][q] = index[key]
+    return t
+
+
+@pytest.mark.parametrize("k,min_freq", [(11, 1), (15, 2), (21, 2), (33, 3)])
+def test_host_contig_walk_over_a_table_equals_the_oracle_walk(k, min_freq):
+    rng = np.random.default_rng(40 + k)
+    reads, _ = sample_reads(rng, n_regions=1, reads_per_region=150, L=70, ref_len=160, sub=0.004, dup=0.1, with_n=0.02)
+    rows, _ = KO.build_graphs(reads, None, k, min_freq)
+    a = KO.Assembler(k, min_freq)
+    a.add_reads(reads)
+    a.filter_low_frequency_nodes(); a.identify_root_nodes()
+    want = a.build_contigs(min_contig_length=k + 5)
+    got = K.contigs_from_table(table_from_oracle_rows(rows, k), k, min_contig_length=k + 5)
+    assert sorted(got) == sorted(want) and got == want       # same contigs, and in the same order: roots and branches in creation order
+    assert len(want) >= 1
