@@ -264,3 +264,45 @@ def test_shared_window_kernel_equals_general_kernel(aligner, monkeypatch):
     for f in FIELDS + ("cigar_n", "flags"):
         assert np.array_equal(a1.results[f], a2.results[f]), f
     assert all(a1.cigar(k) == a2.cigar(k) for k in range(0, len(a1), 37))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_differential(seed):
+    """Random scoring parameters, lengths, repeat structure, N density and window sharing per seed; every record against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    match = int(rng.integers(1, 6)); mismatch = -int(rng.integers(0, 9)); gap_open = int(rng.integers(0, 12)); gap_ext = int(rng.integers(1, 5))
+    params = (match, mismatch, gap_open, gap_ext)
+    n_win = int(rng.integers(5, 60))
+    alphabet = list("ACGT") if seed % 3 else list("ACGTN")
+    pw = None if seed % 3 else [0.245, 0.245, 0.245, 0.245, 0.02]
+    low_complexity = seed % 4 == 1
+    wins = []
+    for _ in range(n_win):
+        W = int(rng.integers(1, 700))
+        if low_complexity:
+            u = "".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 5))))
+            wins.append((u * W)[:W])
+        else:
+            wins.append("".join(rng.choice(alphabet, size=W, p=pw)))
+    reads, idx = [], []
+    for _ in range(int(rng.integers(150, 400))):
+        wi = int(rng.integers(0, n_win)); w = wins[wi]
+        L = int(rng.integers(1, 257))
+        s = int(rng.integers(0, len(w)))
+        r = list(w[s:s + L])
+        r += list(rng.choice(list("ACGT"), size=L - len(r)))
+        k = 0
+        while k < len(r):                                     # substitutions, insertions, deletions
+            u = rng.random()
+            if u < 0.03: r[k] = "ACGT"[int(rng.integers(0, 4))]
+            elif u < 0.04: r[k:k] = list(rng.choice(list("ACGT"), size=int(rng.integers(1, 6))))
+            elif u < 0.05: del r[k:k + int(rng.integers(1, 6))]
+            k += 1
+        r = r[:256] or ["A"]
+        reads.append("".join(r)); idx.append(wi)
+    order = np.argsort(np.array(idx), kind="stable") if seed % 2 else np.arange(len(reads))      # grouped by window or scattered
+    reads = [reads[i] for i in order]; idx = np.array([idx[i] for i in order], dtype=np.uint32)
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    with U.SwAligner(*params) as a:
+        al = a.align(rs, ws, idx)
+    check_against_oracle(al, rs, ws, idx, params)
