@@ -16,6 +16,9 @@ using namespace ubu;
 #ifndef PT
 #define PT 64
 #endif
+#ifndef PGT
+#define PGT 64           // threads per CTA of the general kernel
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at %d: %s\n", #x, __LINE__, cudaGetErrorString(e)); return 1; } } while (0)
 
 int main(int argc, char** argv) {
@@ -54,20 +57,22 @@ int main(int argc, char** argv) {
 
   // general kernel (reference for the checksum)
   {
-    constexpr int GP = 64 / PG;
+    constexpr int GP = PGT / PG;
     const int stride = ((W + 2 * PG + 63) / 64) * 64 + PG;
     const size_t smem = (size_t)GP * stride * 2;
-    auto k = sw_fwd16_kernel<PG, PK, false, true, false, 64>;
+    auto k = sw_fwd16_kernel<PG, PK, false, true, false, PGT>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     float best = 1e9f;
     for (int r = 0; r < reps; ++r) {
       CK(cudaEventRecord(e0));
-      k<<<(pairs + GP - 1) / GP, 64, smem>>>(reads, wins, d_idx, nullptr, n, n, sc, d_o1, stride, nullptr);
+      k<<<(pairs + GP - 1) / GP, PGT, smem>>>(reads, wins, d_idx, nullptr, n, n, sc, d_o1, stride, nullptr);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
     }
     CK(cudaGetLastError());
-    printf("general  G=%d K=%d T=64   : %.3f ms  %.0f GCUPS\n", PG, PK, best, cells / best / 1e6);
+    int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, PGT, smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    printf("general  G=%d K=%d T=%d regs=%d blocks/SM=%d warps/SM=%d : %.3f ms  %.0f GCUPS\n", PG, PK, PGT, fa.numRegs, nb, nb * PGT / 32, best, cells / best / 1e6);
   }
   {
     constexpr int GP = PT / PG;

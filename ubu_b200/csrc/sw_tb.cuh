@@ -28,6 +28,9 @@
 #pragma once
 #include "sw_common.cuh"
 
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+
 namespace ubu {
 
 constexpr int TB_NEG = -0x10000000;
@@ -342,6 +345,20 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
           if (t.qn) nm |= load16n(t.qn, i - 16 - k0);
           if (t.rn) nm |= load16n(t.rn, je - 16 - k0);
         }
+        const int rem = min(16, maxk - k0);
+        if (run + rem * ma < S) {                               // S is out of reach inside this word: take it in one step
+          const uint32_t fields = rem == 16 ? 0x55555555u : (0x55555555u << (2 * (16 - rem)));
+          uint32_t dbits = (x | (x >> 1)) & fields, nbits = 0u;
+          if (HAS_N) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) nbits |= ((nm >> u) & 1u) << (2 * u);
+            nbits &= fields; dbits &= ~nbits;
+          }
+          const int d = __popc(dbits), nn = __popc(nbits);
+          run += (rem - d - nn) * ma + d * mm; mism += d;
+          if (run + (maxk - k0 - rem) * ma < S) done = true;
+          continue;
+        }
 #pragma unroll
         for (int u = 15; u >= 0; --u) {
           const int k = k0 + 15 - u;
@@ -364,7 +381,12 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
     ubu_sw_result r;
     r.score = S; r.ref_start = je - len + 1; r.ref_end = je; r.q_start = ie - len + 1; r.q_end = ie; r.edit_distance = edits;
     r.flags = 0; r.cigar_n = (uint16_t)no;
-    const unsigned off = atomicAdd(a.cig_cursor, (unsigned)no);
+    // CIGAR pool space for the lanes that got here together: one cursor update per warp
+    const cooperative_groups::coalesced_group cg_ = cooperative_groups::coalesced_threads();
+    const unsigned pre = cooperative_groups::exclusive_scan(cg_, (unsigned)no);
+    unsigned base = 0u;
+    if (cg_.thread_rank() == cg_.size() - 1) base = atomicAdd(a.cig_cursor, pre + (unsigned)no);
+    const unsigned off = cg_.shfl(base, cg_.size() - 1) + pre;
     r.cigar_off = off;
     if (off + (unsigned)no <= a.cig_cap) { for (int k = 0; k < no; ++k) a.cig_pool[off + k] = ops[k]; }
     else atomicOr(a.err_flag, 1u);
