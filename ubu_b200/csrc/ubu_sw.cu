@@ -926,13 +926,14 @@ void ubu_sw_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // Sequence.java:10-13 (A=0 C=1 T=2 G=3), :31-41 (LSB first); case-folded, non-ACGT -> N plane (SPEC.md section 1).
 void ubu_sw_pack(const char* text, size_t n, uint8_t* packed, uint8_t* nmask, int* has_n) {
-  static int8_t code[256];
-  static bool init = false;
-  if (!init) {
-    for (int k = 0; k < 256; ++k) code[k] = -1;
-    code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['T'] = code['t'] = 2; code['G'] = code['g'] = 3;
-    init = true;
-  }
+  struct Table { int8_t v[256]; };
+  static const Table tab = [] {                            // initialised once, thread-safe (C++11 static)
+    Table t;
+    for (int k = 0; k < 256; ++k) t.v[k] = -1;
+    t.v['A'] = t.v['a'] = 0; t.v['C'] = t.v['c'] = 1; t.v['T'] = t.v['t'] = 2; t.v['G'] = t.v['g'] = 3;
+    return t;
+  }();
+  const int8_t* code = tab.v;
   memset(packed, 0, (n + 3) / 4);
   if (nmask) memset(nmask, 0, (n + 7) / 8);
   int any = 0;
