@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--slots", default="3,4")
     ap.add_argument("--passes", type=int, default=6)
     ap.add_argument("--detail", action="store_true")
+    ap.add_argument("--ramp", action="store_true", help="quarter- and half-size chunks at both ends of a pass (shorter pipeline fill and drain)")
     a = ap.parse_args()
     n = a.n
     w = WL.uniform("cfg2", n, 76, 500, seed=1002, paired=True)
@@ -41,12 +42,18 @@ def main():
         al = U.SwAligner(device=0, slots=slots)
         for chunk in [int(x) for x in a.chunks.split(",")]:
             bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+            if a.ramp and n >= 4 * chunk:
+                sizes = [chunk // 4, chunk // 4, chunk // 2]
+                body = n - 2 * sum(sizes)
+                sizes = sizes + [chunk] * (body // chunk) + ([body % chunk] if body % chunk else []) + sizes[::-1]
+                edges = np.concatenate([[0], np.cumsum(sizes)])
+                bounds = [(int(edges[k]), int(edges[k + 1])) for k in range(len(sizes))]
             chunks = []
             for lo, hi in bounds:
                 wsl, ix = SH.window_slice(w.windows, w.pair_ref_idx, lo, hi)
                 chunks.append((pin_set(w.reads.slice(lo, hi)), pin_set(wsl), pin(ix)))
             res = U.pinned_empty((n,), U.RESULT_DTYPE)
-            pools = [U.pinned_empty((6 * chunk + 4096,), np.uint32) for _ in bounds]
+            pools = [U.pinned_empty((6 * (hi - lo) + 4096,), np.uint32) for lo, hi in bounds]
             # drain after every pass
             best = 1e9
             for rep in range(a.passes):

@@ -50,7 +50,8 @@ namespace ubu {
 // from the candidate range (a narrower traceback band).
 template <int G, int K>
 __device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA, int stepB, int g, uint32_t tA, uint32_t tB, int LA, int LB,
-                                                       int match, FwdOut* __restrict__ out) {
+                                                       const Scoring& sc, FwdOut* __restrict__ out, const TbPlan& plan) {
+  const int match = sc.match;
   const int scA = (int)(int16_t)(best & 0xFFFFu), scB = (int)(int16_t)(best >> 16);
   unsigned long long keyA = 0ull, keyB = 0ull;
   if (scA > 0) keyA = ((unsigned long long)scA << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)(stepA - g + 1)) << 8) | (unsigned long long)(31 - g);
@@ -61,24 +62,43 @@ __device__ __forceinline__ void fwd_group_argmax_store(uint32_t best, int stepA,
     const unsigned long long ob = __shfl_xor_sync(0xffffffffu, keyB, o, G);
     keyA = oa > keyA ? oa : keyA; keyB = ob > keyB ? ob : keyB;
   }
+  // The group's first lane writes the two records and decides how each task will be traced back (its class list), so no
+  // separate planning pass has to re-read them; an unaligned task (score 0) gets its final record here.
+  int clsA = -1, clsB = -1;
   if (g == 0) {
-    if (tA != 0xFFFFFFFFu) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t t = half ? tB : tA;
+      if (t == 0xFFFFFFFFu) continue;
+      const unsigned long long key = half ? keyB : keyA;
       FwdOut o = {0, 0, 0, 0};
-      if (keyA) {
-        const int lane = 31 - (int)(keyA & 0xFFu);
-        o.score = (int)(keyA >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyA >> 8) & 0xFFFFu));
-        o.i_lo = max(lane * K + 1, (o.score + match - 1) / match); o.i_hi = min(LA, lane * K + K);
+      int cls = -1;
+      if (key) {
+        const int lane = 31 - (int)(key & 0xFFu);
+        o.score = (int)(key >> 32); o.je = (int)(0xFFFFu - (uint32_t)((key >> 8) & 0xFFFFu));
+        o.i_lo = max(lane * K + 1, (o.score + match - 1) / match); o.i_hi = min(half ? LB : LA, lane * K + K);
+        cls = tb_class_of(sc, o, plan.caps);
+      } else {
+        ubu_sw_result r; r.score = 0; r.ref_start = r.ref_end = r.q_start = r.q_end = 0; r.edit_distance = 0;
+        r.cigar_off = 0; r.cigar_n = 0; r.flags = UBU_SW_FLAG_UNALIGNED;
+        plan.res[t] = r;
       }
-      out[tA] = o;
+      out[t] = o;
+      if (half) clsB = cls; else clsA = cls;
     }
-    if (tB != 0xFFFFFFFFu) {
-      FwdOut o = {0, 0, 0, 0};
-      if (keyB) {
-        const int lane = 31 - (int)(keyB & 0xFFu);
-        o.score = (int)(keyB >> 32); o.je = (int)(0xFFFFu - (uint32_t)((keyB >> 8) & 0xFFFFu));
-        o.i_lo = max(lane * K + 1, (o.score + match - 1) / match); o.i_hi = min(LB, lane * K + K);
-      }
-      out[tB] = o;
+  }
+  const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int c = 0; c < TB_CLASSES; ++c) {                                   // one counter update per warp and class
+    const unsigned mA = __ballot_sync(0xffffffffu, clsA == c), mB = __ballot_sync(0xffffffffu, clsB == c);
+    if (mA | mB) {
+      const int leader = __ffs(mA | mB) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader) base = atomicAdd(&plan.counts[c], (unsigned)(__popc(mA) + __popc(mB)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      uint32_t* list = plan.lists + (size_t)c * plan.n_slots;
+      if (clsA == c) list[base + __popc(mA & lt)] = tA;
+      if (clsB == c) list[base + __popc(mA) + __popc(mB & lt)] = tB;
     }
   }
 }
@@ -89,7 +109,7 @@ template <int G, int K, bool HAS_N, bool DEFAULT_SC, bool SEL_GLOBAL, int THREAD
 __global__ void __launch_bounds__(THREADS, UBU_FWD_MIN_BLOCKS)
 sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
                 const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks, Scoring sc,
-                FwdOut* __restrict__ out, int sel_stride, void* __restrict__ gsel) {
+                FwdOut* __restrict__ out, int sel_stride, void* __restrict__ gsel, TbPlan plan) {
   static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide the warp");
   constexpr int GP = THREADS / G;
   using SelT = typename SelType<HAS_N>::type;
@@ -241,7 +261,7 @@ sw_fwd16_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_id
     if (!keep_hi) stepB = s;
   }
 
-  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc.match, out);
+  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc, out, plan);
 }
 
 }  // namespace ubu

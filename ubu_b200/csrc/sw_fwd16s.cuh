@@ -49,7 +49,7 @@ template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
 __global__ void __launch_bounds__(THREADS, UBU_FWDS_MIN_BLOCKS)
 sw_fwd16s_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_idx,
                  const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks, Scoring sc,
-                 FwdOut* __restrict__ out, int sel_stride) {
+                 FwdOut* __restrict__ out, int sel_stride, TbPlan plan) {
   static_assert(G == 4 || G == 8 || G == 16 || G == 32, "G must divide the warp and cover an LDS.128 phase half");
   using LY = FwdsLayout<G, K, HAS_N>;
   constexpr int GP = THREADS / G, KQ = LY::KQ, LU = LY::LU, BU = LY::BU, NB = LY::NB, PAD = LY::PAD;
@@ -219,7 +219,7 @@ sw_fwd16s_kernel(DevSeqs reads, DevSeqs wins, const uint32_t* __restrict__ ref_i
     if (!keep_hi) stepB = s;
   }
 
-  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc.match, out);
+  fwd_group_argmax_store<G, K>(best, stepA, stepB, g, tA, tB, LA, LB, sc, out, plan);
 }
 
 }  // namespace ubu

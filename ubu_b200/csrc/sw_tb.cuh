@@ -21,7 +21,8 @@
 // A comparison that holds in the full matrix involves a cell of the SPEC path (exact in the band);
 // one that fails in the full matrix fails a fortiori with banded values (they are lower bounds).
 //
-// Kernels: tb_plan_kernel sorts tasks into band-width classes; tb_diag_kernel handles the gap-free class;
+// Kernels: the forward kernels' epilogue sorts tasks into band-width classes (tb_class_of, sw_common.cuh); tb_diag_kernel
+// handles the gap-free class;
 // tb_fill_reg_kernel<BW> keeps the band row in registers (BW = 8, 16 or 32 diagonals); wider bands go to
 // tb_rect_kernel (sw_tbrect.cuh); tb_wide_kernel (scalar, global scratch, direction bits) is the last
 // resort (extreme scoring parameters / very long windows only).
@@ -34,11 +35,6 @@
 namespace ubu {
 
 constexpr int TB_NEG = -0x10000000;
-// band-width classes: 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 (registers),
-// 4/5/6: wide bands, systolic rectangle fill (sw_tbrect.cuh) with rows <= rows[c] and width <= wcap[c], 7: scalar last resort
-constexpr int TB_CLASSES = 8;
-struct RectCaps { int rows[3]; int wcap[3]; };
-
 struct TbArgs {
   DevSeqs reads, wins;
   const uint32_t* ref_idx;
@@ -66,49 +62,6 @@ __host__ __device__ __forceinline__ Band make_band(const Scoring& sc, const FwdO
   g.rows = f.i_hi - g.i_first + 1;
   g.c0 = g.i_first + g.d_lo - 1;                                       // 0-based window column of cell (row 0, b = 0)
   return g;
-}
-
-// ---- classify ------------------------------------------------------------------------------
-__global__ void tb_plan_kernel(const uint32_t* __restrict__ order /* nullptr = identity */, uint32_t n_slots, uint32_t n_tasks,
-                               const FwdOut* __restrict__ fwd,
-                               Scoring sc, RectCaps caps, ubu_sw_result* __restrict__ res,
-                               uint32_t* __restrict__ lists /* [TB_CLASSES][n_slots] */, unsigned int* __restrict__ counts) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int cls = -1; uint32_t task = 0xFFFFFFFFu;
-  if (order) { if (idx < n_slots) task = order[idx]; } else if (idx < n_tasks) task = idx;
-  if (task != 0xFFFFFFFFu) {
-    const FwdOut f = fwd[task];
-    if (f.score <= 0) {
-      ubu_sw_result r; r.score = 0; r.ref_start = r.ref_end = r.q_start = r.q_end = 0; r.edit_distance = 0;
-      r.cigar_off = 0; r.cigar_n = 0; r.flags = UBU_SW_FLAG_UNALIGNED;
-      res[task] = r;
-    } else {
-      const int gb = gap_bound(sc, f.i_hi, f.score);
-      const int bw = (f.i_hi - f.i_lo) + 2 * gb + 1;
-      if (gb == 0) cls = 0;
-      else if (bw <= 8) cls = 1;
-      else if (bw <= 16) cls = 2;
-      else if (bw <= 32) cls = 3;
-      else {
-        const int clo = max(1, 1 + f.je - f.i_hi - gb), w = f.je - clo + 1;       // rectangle of sw_tbrect.cuh
-        cls = 7;
-#pragma unroll
-        for (int c = 2; c >= 0; --c) if (f.i_hi <= caps.rows[c] && w <= caps.wcap[c]) cls = 4 + c;
-      }
-    }
-  }
-  const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-  for (int c = 0; c < TB_CLASSES; ++c) {
-    const unsigned m = __ballot_sync(0xffffffffu, cls == c);
-    if (m) {
-      unsigned base = 0;
-      const int leader = __ffs(m) - 1;
-      if ((int)lane == leader) base = atomicAdd(&counts[c], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (cls == c) lists[(size_t)c * n_slots + base + __popc(m & ((1u << lane) - 1u))] = task;
-    }
-  }
 }
 
 // ---- helpers -------------------------------------------------------------------------------

@@ -148,7 +148,7 @@ int sel_stride_for(int wmax, int G) { return ((wmax + 2 * G + 63) / 64) * 64 + G
 
 template <int G, int K, bool HAS_N, bool DEF>
 cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
-                         const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, cudaStream_t st) {
+                         const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, const TbPlan& plan, cudaStream_t st) {
   constexpr int GP = FWD_THREADS / G;
   const int stride = sel_stride_for(L.wmax, G);
   const size_t smem = (size_t)GP * stride * (HAS_N ? 4u : 2u);
@@ -156,7 +156,7 @@ cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs
   const uint32_t grid = (pairs + GP - 1) / GP;
   const uint32_t* ord = order ? order + L.begin : nullptr;
   if (smem > kMaxDynSmem) {            // long windows: selectors in global scratch (sized by the caller)
-    sw_fwd16_kernel<G, K, HAS_N, DEF, true, FWD_THREADS><<<grid, FWD_THREADS, 0, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, gsel);
+    sw_fwd16_kernel<G, K, HAS_N, DEF, true, FWD_THREADS><<<grid, FWD_THREADS, 0, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, gsel, plan);
     return cudaGetLastError();
   }
   auto kern = sw_fwd16_kernel<G, K, HAS_N, DEF, false, FWD_THREADS>;
@@ -164,7 +164,7 @@ cudaError_t launch_fwd_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, nullptr);
+  kern<<<grid, FWD_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, nullptr, plan);
   return cudaGetLastError();
 }
 
@@ -178,7 +178,7 @@ int fwds_sel_stride(int wmax, int G) { return ((wmax + 2 * G + 15) / 16) * 16; }
 // selectors of a CTA do not fit shared memory; the caller then uses the general kernel.
 template <int G, int K, bool HAS_N, bool DEF>
 cudaError_t launch_fwds_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
-                          const uint32_t* order, const Scoring& sc, FwdOut* out, cudaStream_t st) {
+                          const uint32_t* order, const Scoring& sc, FwdOut* out, const TbPlan& plan, cudaStream_t st) {
   constexpr int GP = FWDS_THREADS / G;
   const int stride = fwds_sel_stride(L.wmax, G);
   const size_t smem = FwdsLayout<G, K, HAS_N>::smem_bytes(GP, stride);
@@ -191,21 +191,21 @@ cudaError_t launch_fwds_t(const FwdLaunch& L, const DevSeqs& reads, const DevSeq
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, FWDS_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride);
+  kern<<<grid, FWDS_THREADS, smem, st>>>(reads, wins, idx, ord, L.n_slots, L.n_tasks, sc, out, stride, plan);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& wins, const uint32_t* idx,
-                       const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, cudaStream_t st) {
+                       const uint32_t* order, const Scoring& sc, FwdOut* out, void* gsel, const TbPlan& plan, cudaStream_t st) {
   const bool def = sc.match == 1 && sc.mismatch == -3 && sc.gap_open == 5 && sc.gap_ext == 2;
   if (L.shared_win) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
 #define X(i, l, g, k) \
-      case i * 4: e = launch_fwds_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, st); break; \
-      case i * 4 + 1: e = launch_fwds_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, st); break; \
-      case i * 4 + 2: e = launch_fwds_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, st); break; \
-      case i * 4 + 3: e = launch_fwds_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, st); break;
+      case i * 4: e = launch_fwds_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, plan, st); break; \
+      case i * 4 + 1: e = launch_fwds_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, plan, st); break; \
+      case i * 4 + 2: e = launch_fwds_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, plan, st); break; \
+      case i * 4 + 3: e = launch_fwds_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, plan, st); break;
       UBU_FWD_CFGS(X)
 #undef X
       default: break;
@@ -214,10 +214,10 @@ cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& 
   }
   switch (L.cfg * 4 + (L.has_n ? 1 : 0) + (def ? 2 : 0)) {
 #define X(i, l, g, k) \
-    case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, gsel, st); \
-    case i * 4 + 1: return launch_fwd_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, gsel, st); \
-    case i * 4 + 2: return launch_fwd_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, gsel, st); \
-    case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, gsel, st);
+    case i * 4: return launch_fwd_t<g, k, false, false>(L, reads, wins, idx, order, sc, out, gsel, plan, st); \
+    case i * 4 + 1: return launch_fwd_t<g, k, true, false>(L, reads, wins, idx, order, sc, out, gsel, plan, st); \
+    case i * 4 + 2: return launch_fwd_t<g, k, false, true>(L, reads, wins, idx, order, sc, out, gsel, plan, st); \
+    case i * 4 + 3: return launch_fwd_t<g, k, true, true>(L, reads, wins, idx, order, sc, out, gsel, plan, st);
     UBU_FWD_CFGS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -533,8 +533,10 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   DevSeqs wins{s.d_wp.p, s.d_woff.p, s.d_wlen.p, s.wins_n ? s.d_wn.p : nullptr, s.wins_n ? s.d_wnoff.p : nullptr};
   const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
   const uint32_t* d_order = s.identity_order ? nullptr : s.d_order.p;
+  // the forward kernels' epilogue also sorts the tasks into the traceback class lists (and finishes unaligned ones)
+  const TbPlan plan{s.caps, s.d_res.p, s.d_lists.p, s.d_ctr.p, s.n_slots};
   for (const FwdLaunch& L : s.launches) {
-    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, st));
+    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, plan, st));
     ++s.n_launches;
   }
   CU(h, cudaEventRecord(s.ev[1], st));
@@ -543,8 +545,6 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
   a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 8; a.err_flag = s.d_ctr.p + 9;
   const int max_rows = std::max(s.lmax, 1);
-  tb_plan_kernel<<<(s.n_slots + 255) / 256, 256, 0, st>>>(d_order, s.n_slots, s.n_tasks, s.d_fwd.p, h->sc, s.caps, s.d_res.p, s.d_lists.p, s.d_ctr.p);
-  CU(h, cudaGetLastError()); ++s.n_launches;
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
   CU(h, cudaEventRecord(s.ev_fork, st));
