@@ -377,8 +377,8 @@ def main():
             "alu_pipe_only_peak": peak.get("alu_only_roofline_gcups"),
             "ops_per_cell": 7, "launch_ms": fwd_s * 1e3, "share_of_step": float(np.mean(fwd_ms) / np.mean(ev_ms)),
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu capture
-            # (profiles/fwd16s_r01.txt: 94.54 MB + 7.42 MB); only meaningful for the default 1M-read cfg2 launch
-            "traffic": 102.0e6 if n == 1_000_000 else None, "traffic_unit": "bytes per launch (ncu, profiles/fwd16s_r01.txt)",
+            # (profiles/fwd16s_r01.txt: 94.55 MB + 10.13 MB); only meaningful for the default 1M-read cfg2 launch
+            "traffic": 104.7e6 if n == 1_000_000 else None, "traffic_unit": "bytes per launch (ncu, profiles/fwd16s_r01.txt)",
             "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": 6551.4,
                     "frac": algo_bytes / fwd_s / 1e9 / 6551.4, "note": "not the bound: ~2e-3 B/cell"},
         }
