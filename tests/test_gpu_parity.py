@@ -306,3 +306,55 @@ def test_randomized_differential(seed):
     with U.SwAligner(*params) as a:
         al = a.align(rs, ws, idx)
     check_against_oracle(al, rs, ws, idx, params)
+
+
+def test_full_size_cfg3_properties(aligner):
+    """BASELINE.json configs[2] at full size: 5M x 150 bp reads against 2 kb contig windows (1M windows, ~5 reads per window,
+    scattered over the batch -> the planner groups them by window), built in five shards to bound host memory. Properties that
+    need no oracle over all 5M records, plus an oracle-checked sample."""
+    shards, per, L, W, pool = 5, 1_000_000, 150, 2000, 200_000
+    parts, codes_r, codes_w = [], [], []
+    for k in range(shards):
+        w = WL.uniform("cfg3", per, L, W, n_windows=pool, seed=WL.SEEDS["cfg3"] + k, keep_codes=True)
+        parts.append(w); codes_r.append(w.read_codes[:400]); codes_w.append((w.window_codes, w.pair_ref_idx[:400]))
+    nb_r, nb_w = (L + 3) // 4, (W + 3) // 4
+    reads = U.SeqSet(np.concatenate([p.reads.packed[: per * nb_r] for p in parts]), (np.arange(shards * per, dtype=np.int64) * nb_r).astype(np.uint32),
+                     np.full(shards * per, L, dtype=np.uint16), None, None)
+    wins = U.SeqSet(np.concatenate([p.windows.packed[: pool * nb_w] for p in parts]), (np.arange(shards * pool, dtype=np.int64) * nb_w).astype(np.uint32),
+                    np.full(shards * pool, W, dtype=np.uint16), None, None)
+    idx = np.concatenate([p.pair_ref_idx.astype(np.uint32) + np.uint32(k * pool) for k, p in enumerate(parts)])
+    n = shards * per
+    del parts
+    al = aligner.align(reads, wins, idx)
+    r = al.results
+    assert len(al) == n and int((r["flags"] & 1).sum()) == 0
+    assert int(r["score"].max()) <= L and int(r["score"].min()) > 40
+    assert np.all(r["q_end"] >= r["q_start"]) and np.all(r["ref_end"] >= r["ref_start"]) and np.all(r["ref_end"] <= W) and np.all(r["ref_start"] >= 1)
+    ops = al.cigar_pool
+    assert int(r["cigar_n"].sum()) == ops.shape[0]
+    order = np.argsort(r["cigar_off"], kind="stable")
+    starts = r["cigar_off"][order].astype(np.int64)
+    assert np.array_equal(starts, np.concatenate([[0], np.cumsum(r["cigar_n"][order].astype(np.int64))[:-1]]))      # slices tile the pool
+    task_of_op = np.repeat(order, r["cigar_n"][order].astype(np.int64))
+    lens, kinds = (ops >> 4).astype(np.int64), (ops & 15)
+    qlen = np.bincount(task_of_op, weights=np.where(np.isin(kinds, (0, 1, 4)), lens, 0), minlength=n)
+    rlen = np.bincount(task_of_op, weights=np.where(np.isin(kinds, (0, 2)), lens, 0), minlength=n)
+    gaps = np.bincount(task_of_op, weights=np.where(np.isin(kinds, (1, 2)), lens, 0), minlength=n)
+    assert np.all(qlen == L)
+    assert np.all(rlen == r["ref_end"].astype(np.int64) - r["ref_start"] + 1)
+    assert np.all(r["edit_distance"] >= gaps)
+    # score is consistent with the record: matches - mismatches - gap costs, given NM = mismatches + gap bases
+    aligned = r["q_end"].astype(np.int64) - r["q_start"] + 1
+    ins = np.bincount(task_of_op, weights=np.where(kinds == 1, lens, 0), minlength=n)
+    n_gap_runs = np.bincount(task_of_op, weights=np.isin(kinds, (1, 2)).astype(np.float64), minlength=n)
+    mism = r["edit_distance"] - gaps
+    m_cols = aligned - ins
+    assert np.array_equal(r["score"].astype(np.int64), (m_cols - mism) * 1 - 3 * mism - 5 * n_gap_runs - 2 * gaps)
+    # oracle on the first 400 reads of every shard
+    for k in range(shards):
+        wc, ix = codes_w[k]
+        q = list(codes_r[k]); wi = [wc[int(j)] for j in ix]
+        ores, ocig = O.align_batch(q, wi, None, nthreads=8)
+        for j in range(400):
+            t = k * per + j
+            assert all(int(r[t][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(t) == ocig[j]
