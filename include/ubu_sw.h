@@ -170,6 +170,19 @@ void ubu_sw_pack(const char* text, size_t n, uint8_t* packed, uint8_t* nmask, in
  * character. This is the packer of a pipeline that aligns a million reads in ~6 ms. */
 int ubu_sw_pack_batch(const char* text, const uint64_t* text_off, const uint16_t* len, uint32_t n, uint8_t* packed, const uint32_t* off,
                       uint8_t* nmask, const uint32_t* nmask_off, int threads, uint32_t* n_with_n);
+/* SAM text for a batch of results, the last step of the ordered host merge: one line per read in input order with the fields the
+ * reference's consumers read back from the aligner's SAM (QNAME FLAG RNAME POS MAPQ CIGAR SEQ, NM:i, AS:i; ReAligner.java:1088-1143).
+ * QNAME = qname_prefix + (first_index + k); RNAME = rnames[window] (or "w<window>"), POS = window_pos0[window] + ref_start. */
+typedef struct {
+  const char*        qname_prefix;   /* NULL = "r" */
+  uint64_t           first_index;    /* index of read 0 of this batch in the whole run */
+  const uint32_t*    pair_ref_idx;   /* window of every read (NULL = read k <-> window k) */
+  const char* const* rnames;         /* per window, NULL = "w<index>" */
+  const int64_t*     window_pos0;    /* 0-based start of every window on its reference sequence, NULL = 0 */
+} ubu_sw_sam_names;
+/* Formats on `threads` host threads (0 = all cores) and writes the blocks to file descriptor fd in order (fd < 0: format only). */
+int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* cigar_pool, uint32_t n,
+                     const ubu_sw_sam_names* names, int threads, uint64_t* bytes_written);
 /* ReverseComplementor.java:38-62: A<->T, C<->G, every other byte unchanged. */
 void ubu_sw_revcomp(const char* in, size_t n, char* out);
 /* BAM-encoded ops -> "76M" style text; returns chars written (excluding NUL), "*" for n == 0. */

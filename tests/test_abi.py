@@ -127,3 +127,41 @@ def test_batch_packer_matches_the_numpy_packer():
     off = np.zeros(len(clean), dtype=np.uint64); off[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
     got = U.pack_text_batch(np.frombuffer(b"".join(clean), dtype=np.uint8), off, lens)
     assert got.nmask is None and np.array_equal(got.packed, U.pack_texts(clean).packed[: got.packed.size])
+
+
+def test_sam_writer_formats_records_in_input_order(tmp_path):
+    """ubu_sw_sam_write on hand-made records (no GPU): every line against a Python rendering, across thread counts and the
+    block boundary (16384 reads per block)."""
+    rng = np.random.default_rng(8)
+    n = 40_000
+    texts = ["".join(rng.choice(list("ACGTN"), size=int(rng.integers(0, 90)), p=[.24, .24, .24, .24, .04])) for _ in range(n)]
+    reads = U.pack_texts(texts)
+    res = np.zeros(n, dtype=U.RESULT_DTYPE)
+    pool = []
+    idx = rng.integers(0, 500, size=n).astype(np.uint32)
+    pos0 = rng.integers(0, 10**9, size=500).astype(np.int64)
+    for k in range(n):
+        if k % 7 == 3 or not texts[k]:
+            res[k]["flags"] = 1
+            continue
+        ops = [(int(rng.integers(1, 60)), int(o)) for o in rng.choice([0, 1, 2, 4], size=int(rng.integers(1, 6)))]
+        res[k]["cigar_off"], res[k]["cigar_n"] = len(pool), len(ops)
+        pool += [(ln << 4) | op for ln, op in ops]
+        res[k]["score"], res[k]["ref_start"], res[k]["edit_distance"] = int(rng.integers(1, 250)), int(rng.integers(1, 2000)), int(rng.integers(0, 30))
+    al = U.Alignments(res, np.array(pool, dtype=np.uint32))
+    want = []
+    for k in range(n):
+        seq = texts[k] or "*"
+        if res[k]["flags"] & 1:
+            want.append(f"q{1000 + k}\t4\t*\t0\t0\t*\t*\t0\t0\t{seq}\t*")
+        else:
+            want.append(f"q{1000 + k}\t0\tw{idx[k]}\t{int(pos0[idx[k]]) + int(res[k]['ref_start'])}\t37\t{al.cigar_string(k)}\t*\t0\t0\t{seq}\t*"
+                        f"\tNM:i:{int(res[k]['edit_distance'])}\tAS:i:{int(res[k]['score'])}")
+    for threads in (1, 0, 5):
+        path = tmp_path / f"out{threads}.sam"
+        fd = os.open(str(path), os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        nbytes = U.write_sam(fd, reads, al, idx, first_index=1000, qname_prefix="q", window_pos0=pos0, threads=threads)
+        os.close(fd)
+        text = path.read_text()
+        assert nbytes == len(text.encode()) and text.split("\n")[:-1] == want
+    assert U.write_sam(-1, reads, al, idx, first_index=1000, qname_prefix="q", window_pos0=pos0) == nbytes      # format only

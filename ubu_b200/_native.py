@@ -42,6 +42,11 @@ class Refs(C.Structure):
     ]
 
 
+class SamNames(C.Structure):
+    _fields_ = [("qname_prefix", C.c_char_p), ("first_index", C.c_uint64), ("pair_ref_idx", C.c_void_p), ("rnames", C.c_void_p),
+                ("window_pos0", C.c_void_p)]
+
+
 class KmerParams(C.Structure):
     _fields_ = [("kmer_size", C.c_uint32), ("min_node_frequency", C.c_uint32)]
 
@@ -73,6 +78,7 @@ SYMBOLS = [
     ("ubu_sw_pack", None, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     ("ubu_sw_pack_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_uint32)]),
+    ("ubu_sw_sam_write", C.c_int, [C.c_int, C.POINTER(Seqs), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(SamNames), C.c_int, C.POINTER(C.c_uint64)]),
     ("ubu_sw_revcomp", None, [C.c_char_p, C.c_size_t, C.c_char_p]),
     ("ubu_sw_cigar_string", C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]),
     ("ubu_sw_device_count", C.c_int, []),

@@ -183,3 +183,23 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     weakref.finalize(buf, lib.ubu_sw_host_free, p)
     return arr
+
+
+def write_sam(fd: int, reads: SeqSet, al: Alignments, pair_ref_idx: Optional[np.ndarray] = None, first_index: int = 0,
+              qname_prefix: str = "r", window_pos0: Optional[np.ndarray] = None, threads: int = 0) -> int:
+    """ubu_sw_sam_write: SAM lines for a batch of results in input order (QNAME FLAG RNAME POS MAPQ CIGAR * 0 0 SEQ * NM:i AS:i),
+    formatted on the host's cores and written to file descriptor fd (fd < 0: format only). Returns the bytes produced."""
+    n = len(al)
+    idx = None if pair_ref_idx is None else np.ascontiguousarray(pair_ref_idx, dtype=np.uint32)
+    pos0 = None if window_pos0 is None else np.ascontiguousarray(window_pos0, dtype=np.int64)
+    names = N.SamNames(qname_prefix.encode("ascii"), first_index, None if idx is None else idx.ctypes.data, None,
+                       None if pos0 is None else pos0.ctypes.data)
+    rs = reads.as_struct()
+    res = np.ascontiguousarray(al.results)
+    pool = np.ascontiguousarray(al.cigar_pool, dtype=np.uint32)
+    out = C.c_uint64(0)
+    rc = N.lib().ubu_sw_sam_write(fd, C.byref(rs), res.ctypes.data, pool.ctypes.data if pool.size else None, n, C.byref(names), threads,
+                                  C.byref(out))
+    if rc != N.OK:
+        raise N.UbuSwError(rc)
+    return int(out.value)

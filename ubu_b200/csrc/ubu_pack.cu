@@ -119,3 +119,87 @@ extern "C" int ubu_sw_pack_batch(const char* text, const uint64_t* text_off, con
   if (n_with_n) *n_with_n = with_n.load();
   return UBU_SW_OK;
 }
+
+// ---- SAM text for a batch of results (the ordered host merge's last step) --------------------------------
+// One line per read, input order: QNAME FLAG RNAME POS MAPQ CIGAR * 0 0 SEQ * NM:i AS:i -- the fields the reference's
+// consumers read back from the aligner's SAM (ReAligner.java:1088-1143). Formatting runs on all cores in blocks of reads;
+// blocks are written to the descriptor in order.
+namespace {
+
+inline char* put_u(char* p, uint64_t v) {
+  char tmp[24]; int n = 0;
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char* put_s(char* p, const char* s) { while (*s) *p++ = *s++; return p; }
+
+size_t sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* pool, uint32_t lo, uint32_t hi, const ubu_sw_sam_names* nm,
+                 std::vector<char>& out) {
+  static const char bases[4] = {'A', 'C', 'T', 'G'};      // Sequence.java:10-13
+  static const char opc[] = "MIDNSHP=X";
+  size_t need = 0;
+  for (uint32_t k = lo; k < hi; ++k) need += 160 + (size_t)reads->len[k] + 12 * (size_t)res[k].cigar_n + (nm->qname_prefix ? strlen(nm->qname_prefix) : 0) + 64;
+  out.resize(need);
+  char* p = out.data();
+  for (uint32_t k = lo; k < hi; ++k) {
+    const ubu_sw_result& r = res[k];
+    const bool unal = (r.flags & UBU_SW_FLAG_UNALIGNED) != 0;
+    const uint32_t w = nm->pair_ref_idx ? nm->pair_ref_idx[k] : k;
+    p = put_s(p, nm->qname_prefix ? nm->qname_prefix : "r"); p = put_u(p, nm->first_index + k); *p++ = '\t';
+    p = put_u(p, unal ? 4u : 0u); *p++ = '\t';
+    if (unal) { *p++ = '*'; *p++ = '\t'; *p++ = '0'; *p++ = '\t'; *p++ = '0'; *p++ = '\t'; *p++ = '*'; }
+    else {
+      if (nm->rnames) p = put_s(p, nm->rnames[w]); else { *p++ = 'w'; p = put_u(p, w); }
+      *p++ = '\t';
+      p = put_u(p, (uint64_t)((nm->window_pos0 ? nm->window_pos0[w] : 0) + (int64_t)r.ref_start)); *p++ = '\t';
+      p = put_u(p, 37u); *p++ = '\t';
+      for (uint32_t c = 0; c < r.cigar_n; ++c) { const uint32_t op = pool[r.cigar_off + c]; p = put_u(p, op >> 4); *p++ = opc[(op & 15u) < 9 ? (op & 15u) : 0]; }
+    }
+    *p++ = '\t'; *p++ = '*'; *p++ = '\t'; *p++ = '0'; *p++ = '\t'; *p++ = '0'; *p++ = '\t';
+    const uint8_t* q = reads->packed + reads->off[k];
+    const uint8_t* qn = reads->nmask ? reads->nmask + reads->nmask_off[k] : nullptr;
+    const uint32_t L = reads->len[k];
+    for (uint32_t i = 0; i < L; ++i) *p++ = (qn && ((qn[i >> 3] >> (i & 7)) & 1)) ? 'N' : bases[(q[i >> 2] >> ((i & 3) * 2)) & 3];
+    if (L == 0) *p++ = '*';
+    *p++ = '\t'; *p++ = '*';
+    if (!unal) { p = put_s(p, "\tNM:i:"); p = put_u(p, (uint64_t)r.edit_distance); p = put_s(p, "\tAS:i:"); p = put_u(p, (uint64_t)r.score); }
+    *p++ = '\n';
+  }
+  return (size_t)(p - out.data());
+}
+
+}  // namespace
+
+#include <unistd.h>
+
+extern "C" int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* cigar_pool, uint32_t n,
+                                const ubu_sw_sam_names* names, int threads, uint64_t* bytes_written) {
+  if (bytes_written) *bytes_written = 0;
+  if (n == 0) return UBU_SW_OK;
+  if (!reads || !res || !names || reads->count < n || (n && (!reads->off || !reads->len))) return UBU_SW_ERR_ARG;
+  unsigned nt = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t block = 16384;
+  const uint32_t n_blocks = (n + block - 1) / block;
+  nt = std::min<unsigned>(nt, n_blocks);
+  uint64_t total = 0;
+  // rounds of nt blocks: formatted in parallel, written in order
+  std::vector<std::vector<char>> bufs(nt);
+  std::vector<size_t> used(nt, 0);
+  for (uint32_t b0 = 0; b0 < n_blocks; b0 += nt) {
+    const unsigned m = std::min<unsigned>(nt, n_blocks - b0);
+    std::vector<std::thread> pool;
+    try {
+      for (unsigned t = 0; t < m; ++t)
+        pool.emplace_back([&, t] { const uint32_t lo = (b0 + t) * block, hi = std::min<uint32_t>(n, lo + block); used[t] = sam_block(reads, res, cigar_pool, lo, hi, names, bufs[t]); });
+    } catch (...) { for (auto& th : pool) th.join(); return UBU_SW_ERR_NOMEM; }
+    for (auto& th : pool) th.join();
+    for (unsigned t = 0; t < m; ++t) {
+      size_t off = 0;
+      while (fd >= 0 && off < used[t]) { const ssize_t wr = write(fd, bufs[t].data() + off, used[t] - off); if (wr <= 0) return UBU_SW_ERR_ARG; off += (size_t)wr; }
+      total += used[t];
+    }
+  }
+  if (bytes_written) *bytes_written = total;
+  return UBU_SW_OK;
+}

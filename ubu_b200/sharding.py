@@ -156,12 +156,37 @@ class MultiGpuAligner:
         def work(rank: int):
             try:
                 al = self.aligners[rank]
-                for ch in chunks:
-                    if ch.rank != rank:
-                        continue
+                mine = [ch for ch in chunks if ch.rank == rank]
+                if not hasattr(al, "submit"):                      # plain aligner (tests): one chunk after the other
+                    for ch in mine:
+                        w, ix = window_slice(windows, idx, ch.lo, ch.hi)
+                        r = al.align(reads.slice(ch.lo, ch.hi), w, ix)
+                        merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+                    return
+                # the handle's own pipeline: up to `slots` chunks in flight (upload / kernels / download overlap)
+                inflight = []
+
+                def finish(item):
+                    t, ch, res, pool, args = item
+                    try:
+                        used = al.wait(t)
+                        merger.push(ch.cid, (ch, res, pool[:used]))
+                    except Exception as e:                          # CIGAR pool guess too small: redo this chunk synchronously
+                        if getattr(e, "status", None) != -3:
+                            raise
+                        r = al.align(*args)
+                        merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+
+                for ch in mine:
+                    if len(inflight) == al.slots:
+                        finish(inflight.pop(0))
                     w, ix = window_slice(windows, idx, ch.lo, ch.hi)
-                    r = al.align(reads.slice(ch.lo, ch.hi), w, ix)
-                    merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+                    rs = reads.slice(ch.lo, ch.hi)
+                    res = np.zeros(ch.hi - ch.lo, dtype=RESULT_DTYPE)
+                    pool = np.zeros(6 * (ch.hi - ch.lo) + 4096, dtype=np.uint32)
+                    inflight.append((al.submit(rs, w, ix, res, pool), ch, res, pool, (rs, w, ix)))
+                for item in inflight:
+                    finish(item)
             except Exception as e:  # surfaced on the calling thread
                 errors.append(e)
 
