@@ -358,3 +358,26 @@ def test_full_size_cfg3_properties(aligner):
         for j in range(400):
             t = k * per + j
             assert all(int(r[t][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(t) == ocig[j]
+
+
+def test_multi_gpu_aligner_pipeline_equals_one_call(aligner):
+    """ubu_b200.sharding.MultiGpuAligner on the visible GPUs (chunks in flight through pinned staging, in-place ordered merge)
+    returns what one align_batch call returns, CIGARs included; windows shared across chunk borders, ragged reads, N."""
+    from ubu_b200 import _native as N
+    from ubu_b200 import sharding as SH
+
+    rng = np.random.default_rng(4)
+    base = WL.uniform("mg", 30_011, 100, 700, n_windows=4_000, seed=91, sub_rate=0.03, indel_rate=0.01, keep_codes=True)
+    order = np.argsort(base.pair_ref_idx, kind="stable")
+    codes = base.read_codes[order]
+    codes[rng.random(codes.shape) < 0.002] = 4
+    reads = U.pack_codes([c[: int(rng.integers(60, 101))] for c in codes])
+    idx = base.pair_ref_idx[order]
+    one = aligner.align(reads, base.windows, idx)
+    ndev = N.lib().ubu_sw_device_count()
+    with SH.MultiGpuAligner(list(range(ndev)), chunk=2_500) as m:
+        for _ in range(2):                                  # second call reuses the staging buffers
+            got = m.align(reads, base.windows, idx)
+            for f in FIELDS + ("cigar_n", "flags"):
+                assert np.array_equal(got.results[f], one.results[f]), f
+            assert all(got.cigar(k) == one.cigar(k) for k in range(0, len(one), 13))

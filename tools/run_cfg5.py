@@ -46,6 +46,14 @@ def main():
             shard = max(s - 1, 0)
             t0 = time.perf_counter()
             w = WL.uniform("cfg5", a.reads_per_shard, L, W, n_windows=pool, seed=WL.SEEDS["cfg5"] + 7919 * shard, keep_codes=a.check > 0)
+            # reads arrive grouped by window, as coordinate-sorted input does in the reference (ReAligner.java:237): a chunk then
+            # needs only its own stretch of windows
+            order = np.argsort(w.pair_ref_idx, kind="stable")
+            nb = (L + 3) // 4
+            w.reads = U.SeqSet(np.ascontiguousarray(w.reads.packed[: w.n_tasks * nb].reshape(w.n_tasks, nb)[order]).reshape(-1), w.reads.off, w.reads.len, None, None)
+            w.pair_ref_idx = np.ascontiguousarray(w.pair_ref_idx[order])
+            if w.read_codes is not None:
+                w.read_codes = w.read_codes[order]
             t1 = time.perf_counter()
             al = mga.align(w.reads, w.windows, w.pair_ref_idx)
             t2 = time.perf_counter()

@@ -125,21 +125,52 @@ def gather_to_rank0(parts, n_tasks: int, dist=None) -> Optional[Alignments]:
     return merge_ordered(n_tasks, [p for rank_parts in gathered for p in rank_parts])
 
 
+class _PinnedStage:
+    """Pinned host buffers of one in-flight chunk (inputs and outputs), grown on demand and reused: uploads from and downloads
+    into pinned memory are truly asynchronous, which is what lets a handle's slots overlap."""
+
+    def __init__(self):
+        self.bufs: Dict[str, np.ndarray] = {}
+
+    def _buf(self, key: str, nbytes: int) -> np.ndarray:
+        from .aligner import pinned_empty
+
+        b = self.bufs.get(key)
+        if b is None or b.nbytes < nbytes:
+            b = self.bufs[key] = pinned_empty((max(nbytes, 1) * 5 // 4 + 64,), np.uint8)
+        return b
+
+    def put(self, key: str, arr: np.ndarray) -> np.ndarray:
+        v = self._buf(key, arr.nbytes)[: arr.nbytes].view(arr.dtype).reshape(arr.shape)
+        np.copyto(v, arr)
+        return v
+
+    def empty(self, key: str, n: int, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        return self._buf(key, n * dtype.itemsize)[: n * dtype.itemsize].view(dtype)
+
+    def seqset(self, key: str, s: SeqSet) -> SeqSet:
+        return SeqSet(self.put(key + "p", s.packed), self.put(key + "o", s.off), self.put(key + "l", s.len),
+                      None if s.nmask is None else self.put(key + "n", s.nmask), None if s.nmask is None else self.put(key + "m", s.nmask_off))
+
+
 class MultiGpuAligner:
     """One process driving several GPUs: a host thread and a SwAligner handle per device, chunks dealt round-robin,
-    results merged in input order as they complete."""
+    every handle keeps `slots` chunks in flight through pinned staging buffers, results merged in input order."""
 
     def __init__(self, devices: Sequence[int], chunk: int = 250_000, aligner_factory=None, **params):
         from .aligner import SwAligner
 
-        make = aligner_factory or (lambda dev: SwAligner(device=dev, slots=3, **params))
+        make = aligner_factory or (lambda dev: SwAligner(device=dev, slots=4, **params))
         self.devices, self.chunk = list(devices), chunk
         self.aligners = [make(d) for d in self.devices]
+        self._stages: Dict[int, List[_PinnedStage]] = {}
 
     def close(self) -> None:
         for a in self.aligners:
             if hasattr(a, "close"):
                 a.close()
+        self._stages.clear()
 
     def __enter__(self):
         return self
@@ -150,8 +181,9 @@ class MultiGpuAligner:
     def align(self, reads: SeqSet, windows: SeqSet, idx: Optional[np.ndarray] = None) -> Alignments:
         world = len(self.aligners)
         chunks = plan_chunks(reads.count, self.chunk, world)
-        merger = OrderedMerger(len(chunks))
-        parts, errors = [], []
+        res_all = np.empty(reads.count, dtype=RESULT_DTYPE)       # chunks land in their input-order slice: the merge of the records
+        pools: Dict[int, np.ndarray] = {}
+        errors = []
 
         def work(rank: int):
             try:
@@ -161,30 +193,32 @@ class MultiGpuAligner:
                     for ch in mine:
                         w, ix = window_slice(windows, idx, ch.lo, ch.hi)
                         r = al.align(reads.slice(ch.lo, ch.hi), w, ix)
-                        merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+                        res_all[ch.lo:ch.hi] = r.results; pools[ch.cid] = r.cigar_pool
                     return
-                # the handle's own pipeline: up to `slots` chunks in flight (upload / kernels / download overlap)
+                stages = self._stages.setdefault(rank, [_PinnedStage() for _ in range(al.slots)])
                 inflight = []
 
                 def finish(item):
                     t, ch, res, pool, args = item
                     try:
                         used = al.wait(t)
-                        merger.push(ch.cid, (ch, res, pool[:used]))
+                        res_all[ch.lo:ch.hi] = res; pools[ch.cid] = pool[:used].copy()
                     except Exception as e:                          # CIGAR pool guess too small: redo this chunk synchronously
                         if getattr(e, "status", None) != -3:
                             raise
                         r = al.align(*args)
-                        merger.push(ch.cid, (ch, r.results, r.cigar_pool))
+                        res_all[ch.lo:ch.hi] = r.results; pools[ch.cid] = r.cigar_pool
 
-                for ch in mine:
+                for k, ch in enumerate(mine):
                     if len(inflight) == al.slots:
-                        finish(inflight.pop(0))
+                        finish(inflight.pop(0))                    # frees stage k % slots
+                    st = stages[k % al.slots]
                     w, ix = window_slice(windows, idx, ch.lo, ch.hi)
-                    rs = reads.slice(ch.lo, ch.hi)
-                    res = np.zeros(ch.hi - ch.lo, dtype=RESULT_DTYPE)
-                    pool = np.zeros(6 * (ch.hi - ch.lo) + 4096, dtype=np.uint32)
-                    inflight.append((al.submit(rs, w, ix, res, pool), ch, res, pool, (rs, w, ix)))
+                    rs, ws = st.seqset("r", reads.slice(ch.lo, ch.hi)), st.seqset("w", w)
+                    ixp = None if ix is None else st.put("i", np.ascontiguousarray(ix, dtype=np.uint32))
+                    n = ch.hi - ch.lo
+                    res, pool = st.empty("res", n, RESULT_DTYPE), st.empty("pool", 6 * n + 4096, np.uint32)
+                    inflight.append((al.submit(rs, ws, ixp, res, pool), ch, res, pool, (rs, ws, ixp)))
                 for item in inflight:
                     finish(item)
             except Exception as e:  # surfaced on the calling thread
@@ -193,15 +227,17 @@ class MultiGpuAligner:
         threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
         for t in threads:
             t.start()
-        alive = True
-        while alive:
-            alive = any(t.is_alive() for t in threads)
-            for _, p in merger.pop_ready():
-                parts.append(p)
-            if alive:
-                threads[0].join(timeout=0.005)
-        for _, p in merger.pop_ready():
-            parts.append(p)
+        for t in threads:
+            t.join()
         if errors:
             raise errors[0]
-        return merge_ordered(reads.count, parts)
+        # CIGAR pools in chunk order, offsets rebased into the one pool
+        base = 0
+        ordered = []
+        for ch in chunks:
+            p = pools[ch.cid]
+            if base:
+                res_all["cigar_off"][ch.lo:ch.hi] += np.uint32(base)
+            ordered.append(p)
+            base += int(p.shape[0])
+        return Alignments(res_all, np.concatenate(ordered) if ordered else np.zeros(0, np.uint32))
