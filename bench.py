@@ -361,6 +361,34 @@ def main():
         # the end-to-end results must equal the device-resident ones
         same = all(np.array_equal(res_p[f], res0.results[f]) for f in ("score", "ref_start", "ref_end", "q_start", "q_end", "edit_distance", "cigar_n"))
         e2e["matches_device_resident_results"] = bool(same)
+        # the same measurement through ONE ubu_sw_align_batch call per step (the library cuts the batch into chunks and runs
+        # them through its slots itself): what a caller gets without managing tickets
+        import ctypes as C
+
+        from ubu_b200 import _native as N
+
+        whole_r, whole_w, whole_i = pin_set(w.reads), pin_set(w.windows), None if w.pair_ref_idx is None else pin(w.pair_ref_idx)
+        res_q = U.pinned_empty((n,), U.RESULT_DTYPE); pool_q = U.pinned_empty((6 * n + 4096,), np.uint32)
+        rs_, ws_, used_ = whole_r.as_struct(), whole_w.as_struct(), C.c_size_t(0)
+
+        def one_call():
+            rc = N.lib().ubu_sw_align_batch(al._h, C.byref(rs_), C.byref(ws_), None if whole_i is None else whole_i.ctypes.data,
+                                            res_q.ctypes.data, pool_q.ctypes.data, pool_q.shape[0], C.byref(used_))
+            if rc:
+                raise N.UbuSwError(rc)
+
+        for _ in range(max(args.warmup, 1)):
+            one_call()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            one_call()
+        barrier()
+        oc_s = max_over_ranks(time.perf_counter() - t0)
+        same_q = all(np.array_equal(res_q[f], res0.results[f]) for f in ("score", "ref_start", "ref_end", "q_start", "q_end", "edit_distance", "cigar_n"))
+        e2e["one_call"] = {"value": total_cells / oc_s / 1e9, "unit": "GCUPS", "reads_per_s": total_reads / oc_s,
+                           "how": "one ubu_sw_align_batch call per step on the whole pinned batch; chunking and slot pipeline inside the library",
+                           "matches_device_resident_results": bool(same_q)}
 
     clocks = sampler.stop()
     # ---------------- roofline of the dominant kernel (forward pass) ----------------------------------

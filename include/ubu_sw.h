@@ -83,14 +83,18 @@ typedef struct {
 typedef struct ubu_sw_handle ubu_sw_handle;
 
 /* Stands in for `new Aligner(reference, numThreads)` (Aligner.java:13-16): one handle per GPU.
- * params == NULL -> SPEC defaults. slots = depth of the H2D/compute/D2H pipeline (1..8; 0 -> 2). */
+ * params == NULL -> SPEC defaults. slots = depth of the H2D/compute/D2H pipeline (1..8; 0 -> 4). */
 int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_handle** out);
 void ubu_sw_destroy(ubu_sw_handle* h);
 
 /* Stands in for Aligner.shortAlign / Aligner.align (Aligner.java:18-22,46-56): align read k against
  * window pair_ref_idx[k] (NULL = identity, then reads->count must equal windows->count).
  * out[k] and the CIGAR slice it names describe read k: results are in INPUT order.
- * Synchronous: host->device copies, all kernels and device->host copies complete before return. */
+ * Synchronous: host->device copies, all kernels and device->host copies complete before return.
+ * A large batch (>= 131072 reads, sequences laid out in ascending order, every stretch of reads using a compact stretch of
+ * windows -- what coordinate-sorted input gives) is cut into chunks that travel through the handle's `slots` internally, so
+ * the upload of one chunk, the kernels of the next and the download of a third overlap inside this one call; pinned host
+ * buffers (ubu_sw_host_alloc) make those copies truly asynchronous. Other batches go through in one shot. */
 int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows,
                        const uint32_t* pair_ref_idx, ubu_sw_result* out,
                        uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);

@@ -381,3 +381,37 @@ def test_multi_gpu_aligner_pipeline_equals_one_call(aligner):
             for f in FIELDS + ("cigar_n", "flags"):
                 assert np.array_equal(got.results[f], one.results[f]), f
             assert all(got.cigar(k) == one.cigar(k) for k in range(0, len(one), 13))
+
+
+def test_align_batch_streams_large_batches_identically(monkeypatch):
+    """ubu_sw_align_batch cuts a large batch into chunks that travel through the handle's slots; the records, their order and
+    the CIGARs must equal the one-shot form (UBU_NO_STREAM=1): mates sharing windows, one window per read, N, and a CIGAR
+    pool that is too small on the first try."""
+    cases = []
+    w = WL.uniform("st1", 300_001, 76, 500, seed=61, paired=True, sub_rate=0.02, indel_rate=0.004)
+    cases.append((w.reads, w.windows, w.pair_ref_idx))
+    w = WL.uniform("st2", 150_000, 100, 300, seed=62)                       # idx None: window k belongs to read k
+    cases.append((w.reads, w.windows, None))
+    b = WL.uniform("st3", 140_000, 60, 200, seed=63, paired=True, keep_codes=True)
+    wn = WL.with_n(b, rate=0.003)
+    cases.append((wn.reads, wn.windows, wn.pair_ref_idx))
+    with U.SwAligner(slots=4) as a:
+        for reads, wins, idx in cases:
+            got = a.align(reads, wins, idx)
+            with pytest.raises(U.UbuSwError) as e:                      # a caller-given pool that is too small: status + required size
+                a.align(reads, wins, idx, cigar_cap=reads.count // 2)
+            assert e.value.status == -3
+            again = a.align(reads, wins, idx)                          # the handle is fine afterwards
+            monkeypatch.setenv("UBU_NO_STREAM", "1")
+            want = a.align(reads, wins, idx)
+            monkeypatch.delenv("UBU_NO_STREAM")
+            for other in (got, again):
+                for f in FIELDS + ("cigar_n", "flags"):
+                    assert np.array_equal(other.results[f], want.results[f]), f
+                assert other.cigar_pool.shape[0] == want.cigar_pool.shape[0]
+                order = np.argsort(other.results["cigar_off"], kind="stable")              # slices tile the pool
+                order = order[other.results["cigar_n"][order] > 0]
+                starts = other.results["cigar_off"][order].astype(np.int64)
+                assert np.array_equal(starts, np.concatenate([[0], np.cumsum(other.results["cigar_n"][order].astype(np.int64))[:-1]]))
+                for k in range(0, len(want), 997):
+                    assert other.cigar(k) == want.cigar(k)

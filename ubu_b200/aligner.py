@@ -54,7 +54,7 @@ class SwAligner:
     """One handle = one GPU (ubu_sw_create). Not thread-safe; use one per host thread / GPU."""
 
     def __init__(self, match: int = 1, mismatch: int = -3, gap_open: int = 5, gap_ext: int = 2,
-                 device: int = 0, slots: int = 2):
+                 device: int = 0, slots: int = 4):
         self._lib = N.lib()
         self._h = C.c_void_p()
         p = N.Params(match, mismatch, gap_open, gap_ext)

@@ -96,6 +96,8 @@ struct Slot {
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   DevBuf<unsigned char> d_gsel;          // per-column selectors of forward launches with very long windows
   PinBuf<uint32_t> h_order;
+  PinBuf<uint32_t> h_roff, h_rnoff, h_woff, h_wnoff, h_idx, h_pool;   // pinned scratch of the streamed form of align_batch
+  uint32_t st_lo = 0, st_hi = 0;         // chunk of the streamed batch this slot holds
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
   std::vector<uint32_t> tmp_keys, tmp_end;
@@ -267,7 +269,8 @@ int validate_seqs(const ubu_sw_seqs* s) {
 }
 
 // ---- plan: class per task, order by (class, window length), pad classes to pairs ------------------
-int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx) {
+// trusted = the caller (the streamed align_batch) has already checked every offset and index of this chunk
+int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false) {
   const uint32_t n = reads->count;
   s.identity_order = false;
   // ---- uniform batch (one read-length class, one window length, no N in any window): the common shape of a
@@ -289,11 +292,13 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
     if (n && wins->count && c0 == c1 && wmin == wmax && !win_n) {
       uint32_t bad = 0, imax = 0;
       const uint32_t rbytes = ((uint32_t)lmax + 3u) / 4u, wbytes = ((uint32_t)wmax + 3u) / 4u;
-      for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->off[t] + rbytes > reads->packed_bytes);
-      for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->off[w] + wbytes > wins->packed_bytes);
-      if (idx) { for (uint32_t t = 0; t < n; ++t) imax = std::max(imax, idx[t]); if (imax >= wins->count) bad = 1; }
-      if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)lmax + 7u) / 8u > reads->nmask_bytes);
-      if (wins->nmask) for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->nmask_off[w] + ((uint32_t)wmax + 7u) / 8u > wins->nmask_bytes);
+      if (!trusted) {
+        for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->off[t] + rbytes > reads->packed_bytes);
+        for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->off[w] + wbytes > wins->packed_bytes);
+        if (idx) { for (uint32_t t = 0; t < n; ++t) imax = std::max(imax, idx[t]); if (imax >= wins->count) bad = 1; }
+        if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)lmax + 7u) / 8u > reads->nmask_bytes);
+        if (wins->nmask) for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->nmask_off[w] + ((uint32_t)wmax + 7u) / 8u > wins->nmask_bytes);
+      }
       if (bad) return UBU_SW_ERR_ARG;
       s.lmax = lmax;
       s.n_slots = (n + 1u) & ~1u;
@@ -429,7 +434,7 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
   return UBU_SW_OK;
 }
 
-int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx) {
+int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false) {
   int rc = validate_seqs(reads); if (rc) return rc;
   rc = validate_seqs(wins); if (rc) return rc;
   if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
@@ -439,7 +444,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   s.reads_n = reads->nmask != nullptr; s.wins_n = wins->nmask != nullptr;
   s.any_n = s.reads_n || s.wins_n;
   if (s.n_tasks == 0) { s.n_slots = 0; s.launches.clear(); s.staged = true; return UBU_SW_OK; }
-  rc = plan_batch(h, s, reads, wins, idx); if (rc) return rc;
+  rc = plan_batch(h, s, reads, wins, idx, trusted); if (rc) return rc;
 
   const uint32_t n = s.n_tasks, nw = wins->count;
   {   // launches whose selectors do not fit shared memory keep them in a global scratch (one launch at a time on the stream)
@@ -689,7 +694,7 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
   *out = nullptr;
   ubu_sw_params p = params ? *params : ubu_sw_params{1, -3, 5, 2};
   if (!params_ok(p)) return UBU_SW_ERR_ARG;
-  if (slots == 0) slots = 2;
+  if (slots == 0) slots = 4;
   if (slots < 1 || slots > kMaxSlots) return UBU_SW_ERR_ARG;
   int ndev = ubu_sw_device_count();
   if (device < 0 || device >= ndev) return UBU_SW_ERR_NO_DEVICE;
@@ -726,6 +731,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
     s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release(); s.d_gsel.release();
     s.h_order.release(); s.h_ctr.release();
+    s.h_roff.release(); s.h_rnoff.release(); s.h_woff.release(); s.h_wnoff.release(); s.h_idx.release(); s.h_pool.release();
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
@@ -807,8 +813,142 @@ int ubu_sw_wait(ubu_sw_handle* h, int ticket, size_t* cigar_pool_used) {
   return do_fetch(h, s, s.out, s.pool, s.pool_cap, cigar_pool_used);
 }
 
+// A large batch is cut into chunks that travel through the handle's slots (upload of chunk c+1, kernels of chunk c and download
+// of chunk c-1 overlap); records land in out[] directly, every chunk's CIGAR ops come back through the slot's pinned staging
+// and are appended to the caller's pool in input order with the records' offsets rebased. Needs what every packer produces:
+// sequences laid out in ascending, non-overlapping order. Returns UBU_SW_ERR_BUSY_FALLBACK (internal) when the batch does not
+// qualify and the one-shot path should run instead.
+namespace {
+constexpr int kNoStream = 1;                               // internal: not a streamable batch
+constexpr uint32_t kStreamMinReads = 1u << 17, kStreamChunkMin = 1u << 15, kStreamChunkMax = 1u << 17;
+
+bool ascending(const uint32_t* off, const uint16_t* len, uint32_t n, uint32_t per) {       // per = bases per byte
+  uint32_t bad = 0;
+  for (uint32_t k = 0; k + 1 < n; ++k) bad |= (uint32_t)((uint64_t)off[k] + ((uint32_t)len[k] + per - 1u) / per > off[k + 1]);
+  return !bad;
+}
+
+int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, ubu_sw_result* out,
+                 uint32_t* pool, size_t pool_cap, size_t* used_out) {
+  const uint32_t n = reads->count;
+  if (h->n_slots < 2 || n < kStreamMinReads || !out) return kNoStream;
+  for (int k = 0; k < h->n_slots; ++k) if (h->slots[k].pending) return kNoStream;
+  if (validate_seqs(reads) || validate_seqs(wins) || (!idx && reads->count != wins->count)) return kNoStream;   // the one-shot path reports it
+  const uint32_t chunk = std::min(kStreamChunkMax, std::max(kStreamChunkMin, n / (uint32_t)(2 * h->n_slots)));
+  // What streaming needs is checked chunk by chunk, right before a chunk is staged (a pass over the whole batch up front
+  // would sit in front of the first upload): its reads and the windows they use are laid out in ascending order, and the
+  // windows form a compact stretch (reads grouped by window, as coordinate-sorted input is). A chunk that does not
+  // qualify sends the whole batch to the one-shot path, which has no such needs.
+  // ascending layout check and offset rebasing of one stretch in a single pass; false = not ascending / out of the buffer
+  auto rebase = [](const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per, uint64_t limit, uint32_t* dst, uint32_t& b0, uint32_t& b1) -> bool {
+    b0 = off[0];
+    uint32_t bad = 0;
+    for (uint32_t k = 0; k + 1 < m; ++k) { dst[k] = off[k] - b0; bad |= (uint32_t)((uint64_t)off[k] + ((uint32_t)len[k] + per - 1u) / per > off[k + 1]); }
+    dst[m - 1] = off[m - 1] - b0;
+    const uint64_t end = (uint64_t)off[m - 1] + ((uint32_t)len[m - 1] + per - 1u) / per;
+    b1 = (uint32_t)end;
+    return !bad && end <= limit;
+  };
+  CU(h, cudaSetDevice(h->device));
+  auto fail = [&](int rc) {                                // nothing of this call may still be writing into the caller's buffers
+    for (int k = 0; k < h->n_slots; ++k) if (h->slots[k].stream) cudaStreamSynchronize(h->slots[k].stream);
+    return rc;
+  };
+  size_t base = 0, total = 0;
+  bool overflow = false;
+  int head = 0, inflight = 0;                              // slots are used round-robin: head = oldest in flight
+
+  auto finish = [&](Slot& s) -> int {
+    size_t used = 0;
+    const size_t cap = s.h_pool.cap;
+    int rc = do_fetch(h, s, out + s.st_lo, s.h_pool.p, cap, &used);
+    if (rc == UBU_SW_ERR_CIGAR_POOL) {                     // the 6-ops-per-read guess was too small for this chunk
+      CU(h, s.h_pool.reserve(used + 64));
+      rc = do_fetch(h, s, out + s.st_lo, s.h_pool.p, s.h_pool.cap, &used);
+    }
+    if (rc) return rc;
+    total += used;
+    if (base + used > pool_cap || (used && !pool)) overflow = true;
+    else {
+      if (used) memcpy(pool + base, s.h_pool.p, used * sizeof(uint32_t));
+      if (base) for (uint32_t t = s.st_lo; t < s.st_hi; ++t) out[t].cigar_off += (uint32_t)base;
+      base += used;
+    }
+    return UBU_SW_OK;
+  };
+
+  // chunk borders: quarter- and half-size chunks at both ends shorten the pipeline's fill (nothing overlaps the first upload)
+  // and drain (nothing overlaps the last traceback and download)
+  std::vector<uint32_t> cuts{0u};
+  {
+    const uint32_t ramp[3] = {chunk / 4u, chunk / 4u, chunk / 2u};
+    uint32_t head_end = 0, tail = 0;
+    for (uint32_t r : ramp) { head_end += r; tail += r; }
+    if ((uint64_t)head_end + tail + chunk <= n && !env_off("UBU_STREAM_NORAMP")) {
+      for (uint32_t r : ramp) cuts.push_back(cuts.back() + r);
+      while ((uint64_t)cuts.back() + chunk + tail <= n) cuts.push_back(cuts.back() + chunk);
+      const uint32_t rest = n - tail - cuts.back();
+      if (rest) cuts.push_back(cuts.back() + rest);
+      for (int r = 2; r >= 0; --r) cuts.push_back(cuts.back() + ramp[r]);
+    } else {
+      while (cuts.back() < n) cuts.push_back(std::min<uint64_t>(n, (uint64_t)cuts.back() + chunk));
+    }
+  }
+  for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
+    const uint32_t lo = cuts[ci], hi = cuts[ci + 1], m = hi - lo;
+    if (inflight == h->n_slots) { int rc = finish(h->slots[head]); if (rc) return fail(rc); head = (head + 1) % h->n_slots; --inflight; }
+    Slot& s = h->slots[(head + inflight) % h->n_slots];
+    // ---- this chunk's views: reads [lo, hi) and the stretch of windows they use, offsets rebased to the stretch; a layout
+    //      that is not ascending or a stretch that is not compact sends the whole batch to the one-shot path ----
+    ubu_sw_seqs rs = *reads, ws = *wins;
+    uint32_t b0, b1;
+    CU(h, s.h_roff.reserve(m));
+    if (!rebase(reads->off + lo, reads->len + lo, m, 4, reads->packed_bytes, s.h_roff.p, b0, b1)) return fail(kNoStream);
+    rs.packed = reads->packed + b0; rs.packed_bytes = b1 - b0; rs.off = s.h_roff.p; rs.len = reads->len + lo; rs.count = m;
+    if (reads->nmask) {
+      CU(h, s.h_rnoff.reserve(m));
+      if (!rebase(reads->nmask_off + lo, reads->len + lo, m, 8, reads->nmask_bytes, s.h_rnoff.p, b0, b1)) return fail(kNoStream);
+      rs.nmask = reads->nmask + b0; rs.nmask_bytes = b1 - b0; rs.nmask_off = s.h_rnoff.p;
+    }
+    uint32_t w0 = lo, w1 = hi;                             // windows [w0, w1)
+    const uint32_t* ix = nullptr;
+    if (idx) {
+      uint32_t mn = 0xFFFFFFFFu, mx = 0;
+      for (uint32_t t = lo; t < hi; ++t) { mn = std::min(mn, idx[t]); mx = std::max(mx, idx[t]); }
+      if (mx >= wins->count || (uint64_t)(mx - mn) + 1u > 2ull * m + 16ull) return fail(kNoStream);
+      w0 = mn; w1 = mx + 1u;
+      CU(h, s.h_idx.reserve(m));
+      for (uint32_t k = 0; k < m; ++k) s.h_idx.p[k] = idx[lo + k] - w0;
+      ix = s.h_idx.p;
+    }
+    const uint32_t mw = w1 - w0;
+    CU(h, s.h_woff.reserve(mw));
+    if (!rebase(wins->off + w0, wins->len + w0, mw, 4, wins->packed_bytes, s.h_woff.p, b0, b1)) return fail(kNoStream);
+    ws.packed = wins->packed + b0; ws.packed_bytes = b1 - b0; ws.off = s.h_woff.p; ws.len = wins->len + w0; ws.count = mw;
+    if (wins->nmask) {
+      CU(h, s.h_wnoff.reserve(mw));
+      if (!rebase(wins->nmask_off + w0, wins->len + w0, mw, 8, wins->nmask_bytes, s.h_wnoff.p, b0, b1)) return fail(kNoStream);
+      ws.nmask = wins->nmask + b0; ws.nmask_bytes = b1 - b0; ws.nmask_off = s.h_wnoff.p;
+    }
+    CU(h, s.h_pool.reserve(6u * (size_t)m + 4096u));
+    int rc = do_stage(h, s, &rs, &ws, ix, true); if (rc) return fail(rc);
+    rc = do_run(h, s); if (rc) return fail(rc);
+    rc = enqueue_early_d2h(h, s, out + lo, s.h_pool.p, s.h_pool.cap); if (rc) return fail(rc);
+    s.st_lo = lo; s.st_hi = hi;
+    ++inflight;
+  }
+  while (inflight) { int rc = finish(h->slots[head]); if (rc) return fail(rc); head = (head + 1) % h->n_slots; --inflight; }
+  if (used_out) *used_out = overflow ? total : base;
+  return overflow ? UBU_SW_ERR_CIGAR_POOL : UBU_SW_OK;
+}
+}  // namespace
+
 int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
                        ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used) {
+  if (h && reads && windows && !env_off("UBU_NO_STREAM")) {
+    const int rc = align_stream(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, cigar_pool_used);
+    if (rc != kNoStream) return rc;
+  }
   int ticket = -1;
   int rc = ubu_sw_submit(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, &ticket);
   if (rc) return rc;
