@@ -117,7 +117,7 @@ void Aligner::run(const std::string& input, const std::string& outputSam) {
   if (!handle_) {
     ubu_sw_params p{match_, mismatch_, gapOpen_, gapExt_};
     ubu_sw_handle* h = nullptr;
-    const int rc = ubu_sw_create(&p, device_, 2, &h);
+    const int rc = ubu_sw_create(&p, device_, 0, &h);   // default pipeline depth: large batches stream through it inside align_batch
     if (rc) throw std::runtime_error(std::string("ubu_sw_create: ") + ubu_sw_strerror(rc));
     handle_ = h;
   }
