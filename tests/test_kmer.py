@@ -249,3 +249,19 @@ def test_host_contig_walk_over_a_table_equals_the_oracle_walk(k, min_freq):
     got = K.contigs_from_table(table_from_oracle_rows(rows, k), k, min_contig_length=k + 5)
     assert sorted(got) == sorted(want) and got == want       # same contigs, and in the same order: roots and branches in creation order
     assert len(want) >= 1
+
+
+@pytest.mark.gpu
+def test_device_graph_locked_and_lock_free_slots_agree(monkeypatch):
+    """k <= 63 uses lock-free slots (128-bit CAS), k = 64 the locked protocol; UBU_KMER_LOCKED=1 forces the latter for every k:
+    both must return the same table byte for byte."""
+    rng = np.random.default_rng(21)
+    reads, regions = sample_reads(rng, n_regions=40, reads_per_region=400, L=100, ref_len=300, with_n=0.01)
+    packed = U.pack_texts(reads)
+    for k in (15, 33, 63):
+        with K.KmerGraphBuilder(k, 2) as b:
+            free, s1 = b.build(packed, regions)
+            monkeypatch.setenv("UBU_KMER_LOCKED", "1")
+            locked, s2 = b.build(packed, regions)
+            monkeypatch.delenv("UBU_KMER_LOCKED")
+        assert s1 == s2 and free.tobytes() == locked.tobytes()
