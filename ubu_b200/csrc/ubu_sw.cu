@@ -9,6 +9,7 @@
 #include "sw_post.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -96,8 +97,11 @@ struct Slot {
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   DevBuf<unsigned char> d_gsel;          // per-column selectors of forward launches with very long windows
   PinBuf<uint32_t> h_order;
-  PinBuf<uint32_t> h_roff, h_rnoff, h_woff, h_wnoff, h_idx, h_pool;   // pinned scratch of the streamed form of align_batch
+  PinBuf<uint32_t> h_pool;               // pinned staging of a streamed chunk's CIGAR ops
   uint32_t st_lo = 0, st_hi = 0;         // chunk of the streamed batch this slot holds
+  // A streamed chunk keeps the caller's ABSOLUTE offsets and window indices: the device copies hold only the chunk's stretch,
+  // and the pointers handed to the kernels are moved back by these amounts instead (no host pass rewrites anything).
+  size_t bias_rp = 0, bias_rn = 0, bias_wp = 0, bias_wn = 0; uint32_t bias_w = 0;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
   std::vector<uint32_t> tmp_keys, tmp_end;
@@ -139,6 +143,38 @@ int fail_cuda(ubu_sw_handle* h, cudaError_t e, const char* what) {
 #define CU(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda((h), e__, #call); } while (0)
 
 bool env_off(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
+
+// ---- host passes over a batch's metadata: they sit in front of every upload, so they get AVX2 bodies when the CPU has them ----
+#if defined(__x86_64__)
+#define UBU_AVX2 __attribute__((target("avx2")))
+bool cpu_has_avx2() { static const bool v = __builtin_cpu_supports("avx2"); return v; }
+#else
+#define UBU_AVX2
+bool cpu_has_avx2() { return false; }
+#endif
+template <class T> inline void minmax_body(const T* p, size_t n, T& mn, T& mx) {
+  T a = mn, b = mx;
+  for (size_t k = 0; k < n; ++k) { a = p[k] < a ? p[k] : a; b = p[k] > b ? p[k] : b; }
+  mn = a; mx = b;
+}
+UBU_AVX2 void minmax_u32_avx2(const uint32_t* p, size_t n, uint32_t& mn, uint32_t& mx) { minmax_body(p, n, mn, mx); }
+UBU_AVX2 void minmax_u16_avx2(const uint16_t* p, size_t n, uint16_t& mn, uint16_t& mx) { minmax_body(p, n, mn, mx); }
+inline void minmax_u32(const uint32_t* p, size_t n, uint32_t& mn, uint32_t& mx) { if (cpu_has_avx2()) minmax_u32_avx2(p, n, mn, mx); else minmax_body(p, n, mn, mx); }
+inline void minmax_u16(const uint16_t* p, size_t n, uint16_t& mn, uint16_t& mx) { if (cpu_has_avx2()) minmax_u16_avx2(p, n, mn, mx); else minmax_body(p, n, mn, mx); }
+// sequences k = 0..m-1 at off[k], len[k] bases at `per` bases per byte: laid out in ascending, non-overlapping order?
+inline uint32_t ascending_body(const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per) {
+  uint32_t bad = 0;
+  const uint32_t sh = per == 4u ? 2u : 3u, add = per - 1u;            // per is 4 (2-bit codes) or 8 (N plane)
+  for (uint32_t k = 0; k + 1 < m; ++k) {
+    const uint32_t d = off[k + 1] - off[k], need = ((uint32_t)len[k] + add) >> sh;
+    bad |= (uint32_t)(off[k + 1] < off[k]) | (uint32_t)(d < need);
+  }
+  return bad;
+}
+UBU_AVX2 uint32_t ascending_avx2(const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per) { return ascending_body(off, len, m, per); }
+inline bool ascending(const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per) {
+  return (cpu_has_avx2() ? ascending_avx2(off, len, m, per) : ascending_body(off, len, m, per)) == 0u;
+}
 
 int cfg_of_len(int L) {
   for (int c = 0; c < kNumCfgs; ++c) if (L <= kFwdCfgs[c].lmax) return c;
@@ -269,22 +305,34 @@ int validate_seqs(const ubu_sw_seqs* s) {
 }
 
 // ---- plan: class per task, order by (class, window length), pad classes to pairs ------------------
+// A chunk of a streamed batch (align_stream): the seqs structs keep the caller's full buffers and ABSOLUTE offsets / window
+// indices, only their off / len pointers are advanced to the chunk; the stretch of bytes the chunk really uses (and that is
+// copied to the device) is described here, and the device pointers are moved back by the same amounts in do_run.
+struct StageBias {
+  size_t rp, r_bytes, rn, rn_bytes;      // reads: first byte and byte count in packed / nmask
+  size_t wp, w_bytes, wn, wn_bytes;      // windows
+  uint32_t w;                            // index of the chunk's first window
+};
+
 // trusted = the caller (the streamed align_batch) has already checked every offset and index of this chunk
-int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false) {
+int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false,
+               const StageBias* bias = nullptr) {
+  const uint32_t idx_bias = bias ? bias->w : 0u;
   const uint32_t n = reads->count;
   s.identity_order = false;
   // ---- uniform batch (one read-length class, one window length, no N in any window): the common shape of a
   //      realignment batch. Only bounds are checked (vectorisable passes); tasks keep their input order.
   {
     uint16_t lmin = 0xFFFF, lmax = 0, wmin = 0xFFFF, wmax = 0;
-    for (uint32_t t = 0; t < n; ++t) { const uint16_t L = reads->len[t]; lmin = std::min(lmin, L); lmax = std::max(lmax, L); }
-    for (uint32_t w = 0; w < wins->count; ++w) { const uint16_t W = wins->len[w]; wmin = std::min(wmin, W); wmax = std::max(wmax, W); }
+    minmax_u16(reads->len, n, lmin, lmax);
+    minmax_u16(wins->len, wins->count, wmin, wmax);
     bool win_n = false;
     if (wins->nmask) {
       if (wins->count && (uint64_t)wins->nmask_off[wins->count - 1] + ((uint32_t)wins->len[wins->count - 1] + 7u) / 8u > wins->nmask_bytes) return UBU_SW_ERR_ARG;
       // any N at all in the window planes? (bytes between sequences are zero in every packer of this repo; a stray bit only costs speed)
-      const uint8_t* m = wins->nmask; uint8_t any = 0;
-      for (uint32_t k = 0; k < wins->nmask_bytes; ++k) any |= m[k];
+      const uint8_t* m = wins->nmask + (bias ? bias->wn : 0); uint8_t any = 0;
+      const size_t mbytes = bias ? bias->wn_bytes : wins->nmask_bytes;
+      for (size_t k = 0; k < mbytes; ++k) any |= m[k];
       win_n = any != 0;
     }
     const int c0 = cfg_of_len(lmin), c1 = cfg_of_len(lmax);
@@ -316,7 +364,7 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
           const uint32_t nw = wins->count;
           s.tmp_keys.assign((size_t)2 * nw + 2, 0u);
           uint32_t* cnt = s.tmp_keys.data(); uint32_t* pos = cnt + nw + 1;
-          for (uint32_t t = 0; t < n; ++t) ++cnt[idx[t]];
+          for (uint32_t t = 0; t < n; ++t) ++cnt[idx[t] - idx_bias];
           uint32_t n_pair_slots = 0, n_left = 0;
           for (uint32_t w = 0; w < nw; ++w) { n_pair_slots += cnt[w] & ~1u; n_left += cnt[w] & 1u; }
           const uint32_t left_slots = (n_left + 1u) & ~1u;
@@ -332,7 +380,7 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
             cnt[w] = (c & 1u) ? lp++ : 0xFFFFFFFFu;          // cnt[w] now = the slot of window w's odd read (general launch)
           }
           for (uint32_t t = 0; t < n; ++t) {
-            const uint32_t w = idx[t];
+            const uint32_t w = idx[t] - idx_bias;
             if (pos[w] < endv[w]) order[pos[w]++] = t; else order[cnt[w]] = t;
           }
           if (n_left & 1u) order[s.n_slots - 1] = 0xFFFFFFFFu;
@@ -370,10 +418,12 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
   int lmax = 0;
   for (uint32_t t = 0; t < n; ++t) {
     const int L = reads->len[t];
-    const uint32_t ri = idx ? idx[t] : t;
+    const uint32_t ri = idx ? idx[t] - idx_bias : t;
     if (ri >= wins->count) return UBU_SW_ERR_ARG;
-    if ((uint64_t)reads->off[t] + ((uint32_t)L + 3u) / 4u > reads->packed_bytes) return UBU_SW_ERR_ARG;
-    if (reads->nmask && (uint64_t)reads->nmask_off[t] + ((uint32_t)L + 7u) / 8u > reads->nmask_bytes) return UBU_SW_ERR_ARG;
+    if (!trusted) {
+      if ((uint64_t)reads->off[t] + ((uint32_t)L + 3u) / 4u > reads->packed_bytes) return UBU_SW_ERR_ARG;
+      if (reads->nmask && (uint64_t)reads->nmask_off[t] + ((uint32_t)L + 7u) / 8u > reads->nmask_bytes) return UBU_SW_ERR_ARG;
+    }
     const int c = cfg_of_len(L);
     if (c < 0) return UBU_SW_ERR_TOO_LONG;
     const int W = wins->len[ri];
@@ -434,7 +484,8 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
   return UBU_SW_OK;
 }
 
-int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false) {
+int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, bool trusted = false,
+             const StageBias* bias = nullptr) {
   int rc = validate_seqs(reads); if (rc) return rc;
   rc = validate_seqs(wins); if (rc) return rc;
   if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
@@ -444,7 +495,13 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   s.reads_n = reads->nmask != nullptr; s.wins_n = wins->nmask != nullptr;
   s.any_n = s.reads_n || s.wins_n;
   if (s.n_tasks == 0) { s.n_slots = 0; s.launches.clear(); s.staged = true; return UBU_SW_OK; }
-  rc = plan_batch(h, s, reads, wins, idx, trusted); if (rc) return rc;
+  rc = plan_batch(h, s, reads, wins, idx, trusted, bias); if (rc) return rc;
+  // what goes to the device: the whole buffers, or only the stretch a streamed chunk uses
+  const size_t r_lo = bias ? bias->rp : 0, r_bytes = bias ? bias->r_bytes : reads->packed_bytes;
+  const size_t rn_lo = bias ? bias->rn : 0, rn_bytes = bias ? bias->rn_bytes : reads->nmask_bytes;
+  const size_t w_lo = bias ? bias->wp : 0, w_bytes = bias ? bias->w_bytes : wins->packed_bytes;
+  const size_t wn_lo = bias ? bias->wn : 0, wn_bytes = bias ? bias->wn_bytes : wins->nmask_bytes;
+  s.bias_rp = r_lo; s.bias_rn = rn_lo; s.bias_wp = w_lo; s.bias_wn = wn_lo; s.bias_w = bias ? bias->w : 0u;
 
   const uint32_t n = s.n_tasks, nw = wins->count;
   {   // launches whose selectors do not fit shared memory keep them in a global scratch (one launch at a time on the stream)
@@ -456,10 +513,10 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     }
     if (need) CU(h, s.d_gsel.reserve(need + 64));
   }
-  CU(h, s.d_rp.reserve(reads->packed_bytes + 16)); CU(h, s.d_roff.reserve(n)); CU(h, s.d_rlen.reserve(n));
-  CU(h, s.d_wp.reserve(wins->packed_bytes + 16)); CU(h, s.d_woff.reserve(nw)); CU(h, s.d_wlen.reserve(nw));
-  if (s.reads_n) { CU(h, s.d_rn.reserve(reads->nmask_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
-  if (s.wins_n) { CU(h, s.d_wn.reserve(wins->nmask_bytes + 16)); CU(h, s.d_wnoff.reserve(nw)); }
+  CU(h, s.d_rp.reserve(r_bytes + 16)); CU(h, s.d_roff.reserve(n)); CU(h, s.d_rlen.reserve(n));
+  CU(h, s.d_wp.reserve(w_bytes + 16)); CU(h, s.d_woff.reserve(nw)); CU(h, s.d_wlen.reserve(nw));
+  if (s.reads_n) { CU(h, s.d_rn.reserve(rn_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
+  if (s.wins_n) { CU(h, s.d_wn.reserve(wn_bytes + 16)); CU(h, s.d_wnoff.reserve(nw)); }
   if (idx) CU(h, s.d_idx.reserve(n));
   CU(h, s.d_order.reserve(s.n_slots)); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
   CU(h, s.d_fwd.reserve(n)); CU(h, s.d_res.reserve(n));
@@ -507,18 +564,18 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   }
 
   cudaStream_t st = s.stream;
-  CU(h, cudaMemcpyAsync(s.d_rp.p, reads->packed, reads->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_rp.p, reads->packed + r_lo, r_bytes, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(s.d_roff.p, reads->off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(s.d_rlen.p, reads->len, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(s.d_wp.p, wins->packed, wins->packed_bytes, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(s.d_wp.p, wins->packed + w_lo, w_bytes, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(s.d_woff.p, wins->off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(s.d_wlen.p, wins->len, sizeof(uint16_t) * nw, cudaMemcpyHostToDevice, st));
   if (s.reads_n) {
-    CU(h, cudaMemcpyAsync(s.d_rn.p, reads->nmask, reads->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.d_rn.p, reads->nmask + rn_lo, rn_bytes, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(s.d_rnoff.p, reads->nmask_off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   }
   if (s.wins_n) {
-    CU(h, cudaMemcpyAsync(s.d_wn.p, wins->nmask, wins->nmask_bytes, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.d_wn.p, wins->nmask + wn_lo, wn_bytes, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(s.d_wnoff.p, wins->nmask_off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
   }
   if (idx) CU(h, cudaMemcpyAsync(s.d_idx.p, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
@@ -534,8 +591,10 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   CU(h, cudaEventRecord(s.ev[0], st));
   if (s.n_tasks == 0) { CU(h, cudaEventRecord(s.ev[1], st)); CU(h, cudaEventRecord(s.ev[2], st)); s.ran = true; return UBU_SW_OK; }
   CU(h, cudaMemsetAsync(s.d_ctr.p, 0, 16 * sizeof(unsigned int), st));
-  DevSeqs reads{s.d_rp.p, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
-  DevSeqs wins{s.d_wp.p, s.d_woff.p, s.d_wlen.p, s.wins_n ? s.d_wn.p : nullptr, s.wins_n ? s.d_wnoff.p : nullptr};
+  // (a streamed chunk keeps absolute offsets and window indices: the pointers are moved back instead, see Slot::bias_*)
+  DevSeqs reads{s.d_rp.p - s.bias_rp, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p - s.bias_rn : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
+  DevSeqs wins{s.d_wp.p - s.bias_wp, s.d_woff.p - s.bias_w, s.d_wlen.p - s.bias_w, s.wins_n ? s.d_wn.p - s.bias_wn : nullptr,
+               s.wins_n ? s.d_wnoff.p - s.bias_w : nullptr};
   const uint32_t* idx = s.have_idx ? s.d_idx.p : nullptr;
   const uint32_t* d_order = s.identity_order ? nullptr : s.d_order.p;
   // the forward kernels' epilogue also sorts the tasks into the traceback class lists (and finishes unaligned ones)
@@ -731,7 +790,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
     s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release(); s.d_gsel.release();
     s.h_order.release(); s.h_ctr.release();
-    s.h_roff.release(); s.h_rnoff.release(); s.h_woff.release(); s.h_wnoff.release(); s.h_idx.release(); s.h_pool.release();
+    s.h_pool.release();
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
@@ -822,12 +881,6 @@ namespace {
 constexpr int kNoStream = 1;                               // internal: not a streamable batch
 constexpr uint32_t kStreamMinReads = 1u << 17, kStreamChunkMin = 1u << 15, kStreamChunkMax = 1u << 17;
 
-bool ascending(const uint32_t* off, const uint16_t* len, uint32_t n, uint32_t per) {       // per = bases per byte
-  uint32_t bad = 0;
-  for (uint32_t k = 0; k + 1 < n; ++k) bad |= (uint32_t)((uint64_t)off[k] + ((uint32_t)len[k] + per - 1u) / per > off[k + 1]);
-  return !bad;
-}
-
 int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, ubu_sw_result* out,
                  uint32_t* pool, size_t pool_cap, size_t* used_out) {
   const uint32_t n = reads->count;
@@ -836,18 +889,14 @@ int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* 
   if (validate_seqs(reads) || validate_seqs(wins) || (!idx && reads->count != wins->count)) return kNoStream;   // the one-shot path reports it
   const uint32_t chunk = std::min(kStreamChunkMax, std::max(kStreamChunkMin, n / (uint32_t)(2 * h->n_slots)));
   // What streaming needs is checked chunk by chunk, right before a chunk is staged (a pass over the whole batch up front
-  // would sit in front of the first upload): its reads and the windows they use are laid out in ascending order, and the
-  // windows form a compact stretch (reads grouped by window, as coordinate-sorted input is). A chunk that does not
-  // qualify sends the whole batch to the one-shot path, which has no such needs.
-  // ascending layout check and offset rebasing of one stretch in a single pass; false = not ascending / out of the buffer
-  auto rebase = [](const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per, uint64_t limit, uint32_t* dst, uint32_t& b0, uint32_t& b1) -> bool {
-    b0 = off[0];
-    uint32_t bad = 0;
-    for (uint32_t k = 0; k + 1 < m; ++k) { dst[k] = off[k] - b0; bad |= (uint32_t)((uint64_t)off[k] + ((uint32_t)len[k] + per - 1u) / per > off[k + 1]); }
-    dst[m - 1] = off[m - 1] - b0;
+  // would sit in front of the first upload): its reads and the windows they use are laid out in ascending order, so that
+  // one stretch of bytes holds them all, and the windows form a compact stretch (reads grouped by window, as
+  // coordinate-sorted input is). A chunk that does not qualify sends the whole batch to the one-shot path, which has no
+  // such needs. Nothing is rewritten: a chunk keeps the caller's absolute offsets and window indices (StageBias).
+  auto stretch = [](const uint32_t* off, const uint16_t* len, uint32_t m, uint32_t per, uint64_t limit, size_t& b0, size_t& bytes) -> bool {
     const uint64_t end = (uint64_t)off[m - 1] + ((uint32_t)len[m - 1] + per - 1u) / per;
-    b1 = (uint32_t)end;
-    return !bad && end <= limit;
+    b0 = off[0]; bytes = (size_t)(end - off[0]);
+    return end <= limit && ascending(off, len, m, per);
   };
   CU(h, cudaSetDevice(h->device));
   auto fail = [&](int rc) {                                // nothing of this call may still be writing into the caller's buffers
@@ -856,7 +905,10 @@ int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* 
   };
   size_t base = 0, total = 0;
   bool overflow = false;
-  int head = 0, inflight = 0;                              // slots are used round-robin: head = oldest in flight
+  int head = 0, inflight = 0;
+  const bool trace = env_off("UBU_STREAM_TRACE");
+  double t_prep = 0, t_stage = 0, t_run = 0, t_d2h = 0, t_fin = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };                              // slots are used round-robin: head = oldest in flight
 
   auto finish = [&](Slot& s) -> int {
     size_t used = 0;
@@ -896,48 +948,51 @@ int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* 
   }
   for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
     const uint32_t lo = cuts[ci], hi = cuts[ci + 1], m = hi - lo;
+    double t0 = now();
     if (inflight == h->n_slots) { int rc = finish(h->slots[head]); if (rc) return fail(rc); head = (head + 1) % h->n_slots; --inflight; }
+    t_fin += now() - t0; t0 = now();
     Slot& s = h->slots[(head + inflight) % h->n_slots];
-    // ---- this chunk's views: reads [lo, hi) and the stretch of windows they use, offsets rebased to the stretch; a layout
-    //      that is not ascending or a stretch that is not compact sends the whole batch to the one-shot path ----
+    // ---- this chunk's views: reads [lo, hi) and the stretch of windows they use ----
     ubu_sw_seqs rs = *reads, ws = *wins;
-    uint32_t b0, b1;
-    CU(h, s.h_roff.reserve(m));
-    if (!rebase(reads->off + lo, reads->len + lo, m, 4, reads->packed_bytes, s.h_roff.p, b0, b1)) return fail(kNoStream);
-    rs.packed = reads->packed + b0; rs.packed_bytes = b1 - b0; rs.off = s.h_roff.p; rs.len = reads->len + lo; rs.count = m;
+    StageBias bias{};
+    rs.off = reads->off + lo; rs.len = reads->len + lo; rs.count = m;
+    if (!stretch(rs.off, rs.len, m, 4, reads->packed_bytes, bias.rp, bias.r_bytes)) return fail(kNoStream);
     if (reads->nmask) {
-      CU(h, s.h_rnoff.reserve(m));
-      if (!rebase(reads->nmask_off + lo, reads->len + lo, m, 8, reads->nmask_bytes, s.h_rnoff.p, b0, b1)) return fail(kNoStream);
-      rs.nmask = reads->nmask + b0; rs.nmask_bytes = b1 - b0; rs.nmask_off = s.h_rnoff.p;
+      rs.nmask_off = reads->nmask_off + lo;
+      if (!stretch(rs.nmask_off, rs.len, m, 8, reads->nmask_bytes, bias.rn, bias.rn_bytes)) return fail(kNoStream);
     }
     uint32_t w0 = lo, w1 = hi;                             // windows [w0, w1)
-    const uint32_t* ix = nullptr;
     if (idx) {
       uint32_t mn = 0xFFFFFFFFu, mx = 0;
-      for (uint32_t t = lo; t < hi; ++t) { mn = std::min(mn, idx[t]); mx = std::max(mx, idx[t]); }
+      minmax_u32(idx + lo, m, mn, mx);
       if (mx >= wins->count || (uint64_t)(mx - mn) + 1u > 2ull * m + 16ull) return fail(kNoStream);
       w0 = mn; w1 = mx + 1u;
-      CU(h, s.h_idx.reserve(m));
-      for (uint32_t k = 0; k < m; ++k) s.h_idx.p[k] = idx[lo + k] - w0;
-      ix = s.h_idx.p;
+      bias.w = w0;
     }
     const uint32_t mw = w1 - w0;
-    CU(h, s.h_woff.reserve(mw));
-    if (!rebase(wins->off + w0, wins->len + w0, mw, 4, wins->packed_bytes, s.h_woff.p, b0, b1)) return fail(kNoStream);
-    ws.packed = wins->packed + b0; ws.packed_bytes = b1 - b0; ws.off = s.h_woff.p; ws.len = wins->len + w0; ws.count = mw;
+    ws.off = wins->off + w0; ws.len = wins->len + w0; ws.count = mw;
+    if (!stretch(ws.off, ws.len, mw, 4, wins->packed_bytes, bias.wp, bias.w_bytes)) return fail(kNoStream);
     if (wins->nmask) {
-      CU(h, s.h_wnoff.reserve(mw));
-      if (!rebase(wins->nmask_off + w0, wins->len + w0, mw, 8, wins->nmask_bytes, s.h_wnoff.p, b0, b1)) return fail(kNoStream);
-      ws.nmask = wins->nmask + b0; ws.nmask_bytes = b1 - b0; ws.nmask_off = s.h_wnoff.p;
+      ws.nmask_off = wins->nmask_off + w0;
+      if (!stretch(ws.nmask_off, ws.len, mw, 8, wins->nmask_bytes, bias.wn, bias.wn_bytes)) return fail(kNoStream);
     }
+    const uint32_t* ix = idx ? idx + lo : nullptr;
     CU(h, s.h_pool.reserve(6u * (size_t)m + 4096u));
-    int rc = do_stage(h, s, &rs, &ws, ix, true); if (rc) return fail(rc);
+    t_prep += now() - t0; t0 = now();
+    int rc = do_stage(h, s, &rs, &ws, ix, true, &bias); if (rc) return fail(rc);
+    t_stage += now() - t0; t0 = now();
     rc = do_run(h, s); if (rc) return fail(rc);
+    t_run += now() - t0; t0 = now();
     rc = enqueue_early_d2h(h, s, out + lo, s.h_pool.p, s.h_pool.cap); if (rc) return fail(rc);
+    t_d2h += now() - t0;
     s.st_lo = lo; s.st_hi = hi;
     ++inflight;
   }
-  while (inflight) { int rc = finish(h->slots[head]); if (rc) return fail(rc); head = (head + 1) % h->n_slots; --inflight; }
+  { const double t0 = now();
+    while (inflight) { int rc = finish(h->slots[head]); if (rc) return fail(rc); head = (head + 1) % h->n_slots; --inflight; }
+    t_fin += now() - t0; }
+  if (trace) fprintf(stderr, "[ubu_sw stream] %zu chunks: prep %.2f ms, stage %.2f, run %.2f, d2h-enqueue %.2f, finish (incl. waiting) %.2f\n", cuts.size() - 1,
+                     t_prep * 1e3, t_stage * 1e3, t_run * 1e3, t_d2h * 1e3, t_fin * 1e3);
   if (used_out) *used_out = overflow ? total : base;
   return overflow ? UBU_SW_ERR_CIGAR_POOL : UBU_SW_OK;
 }
