@@ -165,3 +165,18 @@ def test_sam_writer_formats_records_in_input_order(tmp_path):
         text = path.read_text()
         assert nbytes == len(text.encode()) and text.split("\n")[:-1] == want
     assert U.write_sam(-1, reads, al, idx, first_index=1000, qname_prefix="q", window_pos0=pos0) == nbytes      # format only
+
+
+def test_jni_shim_parses_against_the_c_abi():
+    """integration/jni/ubu_sw_jni.c cannot be built here (no JDK), but it must at least be valid C against include/*.h: compiled
+    with -fsyntax-only against a minimal stand-in for jni.h, warnings as errors for argument-type mismatches."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Werror=incompatible-pointer-types", "-Werror=int-conversion",
+                        "-I" + os.path.join(ROOT, "tests", "mock_jni"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "jni", "ubu_sw_jni.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
