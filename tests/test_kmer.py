@@ -265,3 +265,18 @@ def test_device_graph_locked_and_lock_free_slots_agree(monkeypatch):
             locked, s2 = b.build(packed, regions)
             monkeypatch.delenv("UBU_KMER_LOCKED")
         assert s1 == s2 and free.tobytes() == locked.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_device_graph_randomized_differential(seed):
+    """Random k (1..64), filter threshold, region count, read length, error / duplicate / N rates per seed; the whole node table
+    against the oracle."""
+    rng = np.random.default_rng(500 + seed)
+    k = int(rng.integers(1, 65)); mf = int(rng.integers(1, 5))
+    reads, regions = sample_reads(rng, n_regions=int(rng.integers(1, 8)), reads_per_region=int(rng.integers(20, 250)), L=int(rng.integers(30, 140)),
+                                  ref_len=int(rng.integers(60, 400)), sub=float(rng.random() * 0.03), dup=float(rng.random() * 0.4),
+                                  with_n=float(rng.random() * 0.05), ragged=bool(seed % 2))
+    with K.KmerGraphBuilder(k, mf) as b:
+        nodes, skipped = b.build(U.pack_texts(reads), regions)
+    compare_with_oracle(nodes, skipped, reads, regions, k, mf)
