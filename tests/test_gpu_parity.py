@@ -415,3 +415,29 @@ def test_align_batch_streams_large_batches_identically(monkeypatch):
                 assert np.array_equal(starts, np.concatenate([[0], np.cumsum(other.results["cigar_n"][order].astype(np.int64))[:-1]]))
                 for k in range(0, len(want), 997):
                     assert other.cigar(k) == want.cigar(k)
+
+
+def test_mixed_batch_pairs_window_sharing_neighbours(aligner, monkeypatch):
+    """The general plan (several read-length classes, windows of different lengths, some with N): neighbours that share a
+    window go to the query-profile kernel, the rest to the general one; every record against the oracle and against the
+    general-kernel-only run."""
+    rng = np.random.default_rng(33)
+    wins = ["".join(rng.choice(list("ACGTN"), size=int(rng.integers(120, 900)), p=[.2475, .2475, .2475, .2475, .01])) for _ in range(300)]
+    reads, idx = [], []
+    for wi, w in enumerate(wins):                          # coordinate-sorted style: the reads of a window follow each other
+        for _ in range(int(rng.integers(0, 7))):
+            L = int(rng.choice([50, 76, 100, 101, 150, 250]))
+            s = int(rng.integers(0, max(len(w) - L, 1)))
+            r = list(w[s:s + L]) + list(rng.choice(list("ACGT"), size=max(0, L - len(w[s:s + L]))))
+            for p in rng.integers(0, L, size=max(1, L // 40)):
+                r[p] = "ACGT"[int(rng.integers(0, 4))]
+            reads.append("".join(r)); idx.append(wi)
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    idx = np.array(idx, dtype=np.uint32)
+    got = aligner.align(rs, ws, idx)
+    check_against_oracle(got, rs, ws, idx)
+    monkeypatch.setenv("UBU_NO_SHARED_WIN", "1")
+    want = aligner.align(rs, ws, idx)
+    monkeypatch.delenv("UBU_NO_SHARED_WIN")
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(got.results[f], want.results[f]), f

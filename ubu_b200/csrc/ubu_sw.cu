@@ -455,31 +455,47 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       std::stable_sort(lo, lo + cnt[b], [&](uint32_t x, uint32_t y) { return (s.tmp_keys[x] & 0xFFFFu) < (s.tmp_keys[y] & 0xFFFFu); });
     }
     const int cfg = b / 2; const bool has_n = b & 1;
-    // split a bucket whose widths vary a lot so that short windows do not pay the long ones' shared memory
-    uint32_t beg = 0; const uint32_t total = (cnt[b] + 1u) & ~1u;
-    while (beg < total) {
-      uint32_t end = total;
-      if (wmin[b] != wmaxv[b]) {
-        const int w0 = (int)(s.tmp_keys[lo[beg]] & 0xFFFFu);
-        const int limit = std::max(w0 * 2, 512);
-        uint32_t e = beg;
-        while (e < cnt[b] && (int)(s.tmp_keys[lo[e]] & 0xFFFFu) <= limit) ++e;
-        e = (e + 1u) & ~1u;                 // keep pairs intact
-        if (e > total) e = total;
-        if (e < total && e > beg) end = e;
+    const uint32_t total = (cnt[b] + 1u) & ~1u;
+    // Neighbours that share a window (mates, coordinate-sorted reads of one region) are paired up for the query-profile kernel;
+    // the others follow in a general-kernel stretch. Both stretches keep the bucket's order (ascending window length).
+    uint32_t n_shared = 0;
+    if (idx && !env_off("UBU_NO_SHARED_WIN")) {
+      std::vector<uint32_t>& rest = s.tmp_end;
+      rest.clear();
+      uint32_t k = 0;
+      while (k < cnt[b]) {
+        if (k + 1 < cnt[b] && idx[lo[k]] == idx[lo[k + 1]]) { lo[n_shared] = lo[k]; lo[n_shared + 1] = lo[k + 1]; n_shared += 2; k += 2; }
+        else rest.push_back(lo[k++]);                       // (writes to lo[] trail the read position: n_shared <= k)
       }
-      int wm = 0;
-      for (uint32_t k = beg; k < end && k < cnt[b]; ++k) wm = std::max(wm, (int)(s.tmp_keys[lo[k]] & 0xFFFFu));
-      FwdLaunch L{cfg, has_n, start[b] + beg, end - beg, wm, 0u};
-      if (idx && !env_off("UBU_NO_SHARED_WIN")) {            // pairs whose two tasks share a window (mates, reads of one contig)
-        bool sh = true;
-        for (uint32_t k = beg; sh && k + 1 < end; k += 2)
-          if (lo[k] != 0xFFFFFFFFu && lo[k + 1] != 0xFFFFFFFFu && idx[lo[k]] != idx[lo[k + 1]]) sh = false;
-        L.shared_win = sh;
-      }
-      s.launches.push_back(L);
-      beg = end;
+      std::copy(rest.begin(), rest.end(), lo + n_shared);
+      if (rest.size() & 1u) lo[n_shared + rest.size()] = 0xFFFFFFFFu;
     }
+    // split a stretch whose widths vary a lot so that short windows do not pay the long ones' shared memory
+    auto add_launches = [&](uint32_t first, uint32_t count_real, bool shared) {
+      const uint32_t stretch_total = (count_real + 1u) & ~1u;
+      uint32_t beg = 0;
+      while (beg < stretch_total) {
+        uint32_t end = stretch_total;
+        if (wmin[b] != wmaxv[b]) {
+          const int w0 = (int)(s.tmp_keys[lo[first + beg]] & 0xFFFFu);
+          const int limit = std::max(w0 * 2, 512);
+          uint32_t e = beg;
+          while (e < count_real && (int)(s.tmp_keys[lo[first + e]] & 0xFFFFu) <= limit) ++e;
+          e = (e + 1u) & ~1u;                 // keep pairs intact
+          if (e > stretch_total) e = stretch_total;
+          if (e < stretch_total && e > beg) end = e;
+        }
+        int wm = 0;
+        for (uint32_t k = beg; k < end && k < count_real; ++k) wm = std::max(wm, (int)(s.tmp_keys[lo[first + k]] & 0xFFFFu));
+        FwdLaunch L{cfg, has_n, start[b] + first + beg, end - beg, wm, 0u};
+        L.shared_win = shared;
+        s.launches.push_back(L);
+        beg = end;
+      }
+    };
+    if (n_shared) add_launches(0u, n_shared, true);
+    if (cnt[b] > n_shared) add_launches(n_shared, cnt[b] - n_shared, false);
+    (void)total;
   }
   return UBU_SW_OK;
 }
