@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libubu_sw.so")
+LIB_PATH = os.environ.get("UBU_SW_LIB") or os.path.join(HERE, "libubu_sw.so")      # UBU_SW_LIB: try another build of the library
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_CIGAR_POOL, ERR_TOO_LONG, ERR_NO_DEVICE, ERR_BUSY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7

@@ -28,8 +28,11 @@ __device__ __forceinline__ RectGeom make_rect(const Scoring& sc, const FwdOut& f
 }
 
 // scratch: one block of wcap * (G*K) words per GROUP, cell (row0, k) at block[k * (G*K) + row0]
+#ifndef UBU_TBR_MIN_BLOCKS
+#define UBU_TBR_MIN_BLOCKS 8
+#endif
 template <int G, int K, bool HAS_N, bool DEFAULT_SC, int THREADS>
-__global__ void __launch_bounds__(THREADS, 8)
+__global__ void __launch_bounds__(THREADS, UBU_TBR_MIN_BLOCKS)
 tb_rect_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
                uint32_t* __restrict__ scratch, uint32_t* __restrict__ opscratch, int wcap, int sel_stride) {
   static_assert(K % 4 == 0, "K must be a multiple of 4 (16-byte stores)");

@@ -35,7 +35,10 @@ constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
 constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
-constexpr int TBR_THREADS = 64, TBR_GRID_PER_SM = 8;     // wide bands: systolic rectangle fill, three (rows, G, K) classes
+#ifndef UBU_TBR_MIN_BLOCKS
+#define UBU_TBR_MIN_BLOCKS 8
+#endif
+constexpr int TBR_THREADS = 64, TBR_GRID_PER_SM = UBU_TBR_MIN_BLOCKS;     // wide bands: systolic rectangle fill, three (rows, G, K) classes
 struct RectCfg { int rows, G, K; };
 const RectCfg kRectCfgs[3] = {{96, 8, 12}, {160, 8, 20}, {256, 16, 16}};
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
