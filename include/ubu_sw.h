@@ -192,6 +192,12 @@ void ubu_sw_revcomp(const char* in, size_t n, char* out);
 /* BAM-encoded ops -> "76M" style text; returns chars written (excluding NUL), "*" for n == 0. */
 int  ubu_sw_cigar_string(const uint32_t* ops, uint32_t n, char* buf, size_t cap);
 
+/* Diagnostics, no GPU needed: the host plan of a batch (which forward launches it would get, in which order its tasks would
+ * run). launches_out: 6 ints per launch = {rows of the length class, has_n, first slot, slots, widest window, shared_window};
+ * order_out[slot] = task (0xFFFFFFFF = padding). UBU_SW_ERR_CAPACITY if a buffer is too small (counts are still written). */
+int ubu_sw_debug_plan(const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx, uint32_t* order_out,
+                      size_t order_cap, uint32_t* n_slots, int* identity, int32_t* launches_out, int launches_cap, int* n_launches);
+
 int          ubu_sw_device_count(void);
 unsigned     ubu_sw_version(void);
 const char*  ubu_sw_strerror(int status);

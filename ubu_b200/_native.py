@@ -81,6 +81,8 @@ SYMBOLS = [
     ("ubu_sw_sam_write", C.c_int, [C.c_int, C.POINTER(Seqs), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(SamNames), C.c_int, C.POINTER(C.c_uint64)]),
     ("ubu_sw_revcomp", None, [C.c_char_p, C.c_size_t, C.c_char_p]),
     ("ubu_sw_cigar_string", C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]),
+    ("ubu_sw_debug_plan", C.c_int, [C.POINTER(Seqs), C.POINTER(Seqs), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_int),
+                                    C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     ("ubu_sw_device_count", C.c_int, []),
     ("ubu_sw_version", C.c_uint, []),
     ("ubu_sw_strerror", C.c_char_p, [C.c_int]),

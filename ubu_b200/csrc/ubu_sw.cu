@@ -107,7 +107,7 @@ struct Slot {
   size_t bias_rp = 0, bias_rn = 0, bias_wp = 0, bias_wn = 0; uint32_t bias_w = 0;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
-  std::vector<uint32_t> tmp_keys, tmp_end;
+  std::vector<uint32_t> tmp_keys, tmp_end, plain_order;     // plain_order: the order array when planning without a device
   // staged batch
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
@@ -373,7 +373,8 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
           const uint32_t left_slots = (n_left + 1u) & ~1u;
           s.n_slots = n_pair_slots + left_slots;
           if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots, 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
-          uint32_t* order = s.h_order.p;
+          else s.plain_order.assign(std::max<size_t>(s.n_slots, 2), 0u);
+          uint32_t* order = h ? s.h_order.p : s.plain_order.data();
           std::vector<uint32_t>& endv = s.tmp_end;           // endv[w]: end of window w's pair slots
           endv.resize(nw);
           uint32_t pp = 0, lp = n_pair_slots;
@@ -443,7 +444,8 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
   for (int b = 0; b < NB; ++b) start[b + 1] = start[b] + ((cnt[b] + 1u) & ~1u);
   s.n_slots = start[NB];
   if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots, 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
-  uint32_t* order = s.h_order.p;
+  else s.plain_order.assign(std::max<size_t>(s.n_slots, 2), 0u);
+  uint32_t* order = h ? s.h_order.p : s.plain_order.data();
   uint32_t fill[NB];
   for (int b = 0; b < NB; ++b) fill[b] = start[b];
   for (uint32_t t = 0; t < n; ++t) order[fill[s.tmp_keys[t] >> 16]++] = t;
@@ -1128,6 +1130,37 @@ int ubu_sw_project_batch(ubu_sw_handle* h, const ubu_sw_contig* contigs, uint32_
   if (cigar_pool_used) *cigar_pool_used = used;
   if (used > cigar_pool_cap) return UBU_SW_ERR_CIGAR_POOL;
   if (used) CU(h, cudaMemcpy(cigar_pool, d_pool, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost));
+  return UBU_SW_OK;
+}
+
+// Device-free view of the host plan (diagnostics and CPU tests): which forward launches a batch would get and in which order
+// its tasks would run. launches_out: 6 ints per launch = {rows of the length class (G*K), has_n, first slot, slots, widest window,
+// shared_window}; order_out: task of every slot (0xFFFFFFFF = padding), identity when *identity is set.
+int ubu_sw_debug_plan(const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx, uint32_t* order_out,
+                      size_t order_cap, uint32_t* n_slots, int* identity, int32_t* launches_out, int launches_cap, int* n_launches) {
+  if (!reads || !windows || !n_slots || !n_launches) return UBU_SW_ERR_ARG;
+  int rc = validate_seqs(reads); if (rc) return rc;
+  rc = validate_seqs(windows); if (rc) return rc;
+  if (!pair_ref_idx && reads->count != windows->count) return UBU_SW_ERR_ARG;
+  Slot s;
+  *n_slots = 0; *n_launches = 0;
+  if (identity) *identity = 0;
+  if (reads->count == 0) return UBU_SW_OK;
+  rc = plan_batch(nullptr, s, reads, windows, pair_ref_idx); if (rc) return rc;
+  *n_slots = s.n_slots; *n_launches = (int)s.launches.size();
+  if (identity) *identity = s.identity_order ? 1 : 0;
+  if (order_out) {
+    if (order_cap < s.n_slots) return UBU_SW_ERR_CAPACITY;
+    for (uint32_t k = 0; k < s.n_slots; ++k) order_out[k] = s.identity_order ? (k < reads->count ? k : 0xFFFFFFFFu) : s.plain_order[k];
+  }
+  if (launches_out) {
+    if (launches_cap < (int)s.launches.size()) return UBU_SW_ERR_CAPACITY;
+    for (size_t k = 0; k < s.launches.size(); ++k) {
+      const FwdLaunch& L = s.launches[k];
+      int32_t* o = launches_out + 6 * k;
+      o[0] = kFwdCfgs[L.cfg].G * kFwdCfgs[L.cfg].K; o[1] = L.has_n ? 1 : 0; o[2] = (int32_t)L.begin; o[3] = (int32_t)L.n_slots; o[4] = L.wmax; o[5] = L.shared_win ? 1 : 0;
+    }
+  }
   return UBU_SW_OK;
 }
 
