@@ -52,6 +52,16 @@ def test_uniform_sets(aligner, name, n, L, W, paired):
     check_against_oracle(al, w.reads, w.windows, w.pair_ref_idx)
 
 
+def test_mixed_read_lengths_one_class_equal_windows_exact_buffers(aligner):
+    """Regression (uniform fast path): trimmed reads of one length class against equal-length windows, shortest read last."""
+    rng = np.random.default_rng(31)
+    wins_t = ["".join(rng.choice(list("ACGT"), size=300)) for _ in range(40)]
+    reads_t = [wins_t[k][50:50 + L] for k, L in enumerate([104] * 20 + [103, 102, 101] * 6 + [100, 99])]
+    reads, wins = U.pack_texts(reads_t), U.pack_texts(wins_t)
+    al = aligner.align(reads, wins)
+    check_against_oracle(al, reads, wins, None)
+
+
 def test_mixed_lengths_indel_rich(aligner):
     w = WL.cfg4(700, seed=5)
     al = aligner.align(w.reads, w.windows, w.pair_ref_idx)

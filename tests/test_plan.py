@@ -103,3 +103,23 @@ def test_plan_rejects_bad_batches_and_handles_empty_ones():
     long_read = U.pack_texts(["A" * 300])
     ls = long_read.as_struct()
     assert N.lib().ubu_sw_debug_plan(C.byref(ls), C.byref(ws), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_TOO_LONG
+
+
+def test_mixed_read_lengths_in_one_class_with_exactly_sized_buffers():
+    """Regression: the uniform fast path (one length class, one window length) bound-checked every read with the bytes of the
+    LONGEST read; with exactly sized packed buffers and the shortest read last it rejected a valid batch."""
+    reads = U.pack_texts(["A" * 104, "C" * 104, "G" * 101, "T" * 100])
+    wins = U.pack_texts(["ACGT" * 75] * 4)
+    assert reads.packed.size == 26 + 26 + 26 + 25                                   # exact: no slack behind the last read
+    order, ident, launches = plan(reads, wins, None)
+    assert ident and len(launches) == 1 and launches[0][0] == 104
+    check_invariants(reads, wins, None, order, launches)
+    # the same with an N plane on the reads
+    reads_n = U.pack_texts(["A" * 104, "C" * 104, "G" * 101, "TTNT" * 25])
+    order, ident, launches = plan(reads_n, wins, None)
+    check_invariants(reads_n, wins, None, order, launches)
+    # and a genuinely short buffer is still rejected
+    rs, ws = reads.as_struct(), wins.as_struct()
+    rs.packed_bytes -= 1
+    n_slots, nl = C.c_uint32(0), C.c_int(0)
+    assert N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_ARG

@@ -342,12 +342,13 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
     if (n && wins->count && c1 < 0) return UBU_SW_ERR_TOO_LONG;
     if (n && wins->count && c0 == c1 && wmin == wmax && !win_n) {
       uint32_t bad = 0, imax = 0;
-      const uint32_t rbytes = ((uint32_t)lmax + 3u) / 4u, wbytes = ((uint32_t)wmax + 3u) / 4u;
+      const uint32_t wbytes = ((uint32_t)wmax + 3u) / 4u;
       if (!trusted) {
-        for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->off[t] + rbytes > reads->packed_bytes);
+        // every read is checked with ITS OWN length: reads of one class may differ in length, and packed_bytes is exact
+        for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->off[t] + ((uint32_t)reads->len[t] + 3u) / 4u > reads->packed_bytes);
         for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->off[w] + wbytes > wins->packed_bytes);
         if (idx) { for (uint32_t t = 0; t < n; ++t) imax = std::max(imax, idx[t]); if (imax >= wins->count) bad = 1; }
-        if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)lmax + 7u) / 8u > reads->nmask_bytes);
+        if (reads->nmask) for (uint32_t t = 0; t < n; ++t) bad |= (uint32_t)((uint64_t)reads->nmask_off[t] + ((uint32_t)reads->len[t] + 7u) / 8u > reads->nmask_bytes);
         if (wins->nmask) for (uint32_t w = 0; w < wins->count; ++w) bad |= (uint32_t)((uint64_t)wins->nmask_off[w] + ((uint32_t)wmax + 7u) / 8u > wins->nmask_bytes);
       }
       if (bad) return UBU_SW_ERR_ARG;
