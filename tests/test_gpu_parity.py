@@ -29,6 +29,43 @@ def check_against_oracle(al: U.Alignments, reads: U.SeqSet, windows: U.SeqSet, i
     assert not bad, f"{len(bad)}/{n} tasks differ; first: {bad[:3]}"
 
 
+def check_every_record_fast(al: U.Alignments, w, params=(1, -3, 5, 2), nthreads=16):
+    """Every record and every CIGAR of a large run against the oracle, vectorised (no per-task Python work except unpacking)."""
+    import ctypes as C
+
+    n = w.n_tasks
+    rl, wl = w.reads.len.astype(np.uint32), w.windows.len.astype(np.uint32)
+    def flat(sq):
+        ln = sq.len.astype(np.int64)
+        seq = np.repeat(np.arange(sq.count), ln)
+        start = np.concatenate([[0], np.cumsum(ln)[:-1]])
+        pos = np.arange(int(ln.sum())) - start[seq]
+        codes = (sq.packed[sq.off.astype(np.int64)[seq] + pos // 4] >> ((pos % 4) * 2).astype(np.uint8)) & 3
+        if sq.nmask is not None:
+            codes = np.where((sq.nmask[sq.nmask_off.astype(np.int64)[seq] + pos // 8] >> (pos % 8).astype(np.uint8)) & 1, 4, codes)
+        return np.ascontiguousarray(codes, dtype=np.uint8), start.astype(np.uint64)
+    q, qoff = flat(w.reads); r, roff = flat(w.windows)
+    idx = None if w.pair_ref_idx is None else np.ascontiguousarray(w.pair_ref_idx, dtype=np.uint32)
+    res = np.zeros(n, dtype=O.SWO_RESULT)
+    stride = int(rl.max()) + 8
+    cig = np.zeros(n * stride, dtype=np.uint32)
+    p = O.SwoParams(*params)
+    st = O.lib().swo_align_batch(q.ctypes.data, qoff.ctypes.data, rl.ctypes.data, r.ctypes.data, roff.ctypes.data, wl.ctypes.data,
+                                 None if idx is None else idx.ctypes.data, n, C.byref(p), res.ctypes.data, cig.ctypes.data, stride, nthreads)
+    assert st == 0
+    g = al.results
+    for f in FIELDS:
+        bad = np.nonzero(g[f] != res[f])[0]
+        assert bad.size == 0, f"{bad.size}/{n} records differ in {f}; first task {bad[:5]}: gpu {g[f][bad[:5]]} oracle {res[f][bad[:5]]}"
+    assert np.array_equal(g["flags"] & 1, (res["flags"] & 1).astype(g["flags"].dtype))
+    assert np.array_equal(g["cigar_n"].astype(np.int64), res["cigar_n"].astype(np.int64))
+    cn = res["cigar_n"].astype(np.int64)
+    task = np.repeat(np.arange(n), cn)
+    k = np.arange(int(cn.sum())) - np.concatenate([[0], np.cumsum(cn)[:-1]])[task]
+    assert np.array_equal(al.cigar_pool[g["cigar_off"].astype(np.int64)[task] + k], cig[task * stride + k]), "CIGAR ops differ"
+    return res
+
+
 @pytest.fixture(scope="module")
 def aligner():
     with U.SwAligner() as a:
@@ -177,6 +214,24 @@ def test_full_size_cfg2_properties(aligner):
     ores, ocig = O.align_batch(q, wi, None, nthreads=8)
     for j, k in enumerate(pick):
         assert all(int(r[int(k)][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(int(k)) == ocig[j]
+
+
+def test_full_cfg1_every_record(aligner):
+    """BASELINE.json configs[0] in full: 10,000 x 100 bp reads vs 10,000 distinct 1 kb windows, every record and CIGAR vs the oracle."""
+    w = WL.cfg1(10_000)
+    al = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    res = check_every_record_fast(al, w)
+    assert int((res["flags"] & 1).sum()) == 0 and int(res["score"].min()) > 30
+
+
+def test_cfg4_120k_every_record_with_tie_stress(aligner):
+    """BASELINE.json configs[3]: 120,000 mixed 50-250 bp indel-rich reads (wide traceback bands) including a 20,000-read
+    tie-stress subset (homopolymer windows, tandem repeats, reads with two equal-score placements); every record and CIGAR
+    vs the oracle. This is the tie-break parity stress config and the slowest path of the library."""
+    w = WL.cfg4(120_000, tie_stress=20_000)
+    al = aligner.align(w.reads, w.windows, w.pair_ref_idx)
+    res = check_every_record_fast(al, w)
+    assert int(res["cigar_n"].max()) >= 7                      # gapped CIGARs are in the set
 
 
 def test_extreme_scoring_reaches_the_scalar_last_resort():

@@ -135,17 +135,26 @@ def pack_texts(texts: Iterable[Union[str, bytes]], force_nmask: bool = False) ->
 
 
 def pack_uniform(codes: np.ndarray) -> SeqSet:
-    """Fast path for a [count, length] uint8 code matrix without N (synthetic workloads)."""
+    """Fast path for a [count, length] uint8 code matrix (synthetic workloads); codes >= 4 are N and go to the bit plane."""
     n, L = codes.shape
     nb = (L + 3) // 4
     pad = nb * 4 - L
-    c = np.pad(codes, ((0, 0), (0, pad))) if pad else codes
+    isn = codes >= 4
+    has_n = bool(isn.any())
+    c = np.where(isn, 0, codes).astype(np.uint8) if has_n else codes
+    c = np.pad(c, ((0, 0), (0, pad))) if pad else c
     c = c.reshape(n, nb, 4).astype(np.uint8)
     packed = (c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6)).astype(np.uint8).reshape(-1)
     if n * nb >= 2 ** 32:
         raise ValueError("batch larger than 4 GiB packed; split it")
     off = (np.arange(n, dtype=np.int64) * nb).astype(np.uint32)
-    return SeqSet(np.ascontiguousarray(packed), off, np.full(n, L, dtype=np.uint16), None, None)
+    nmask = nmask_off = None
+    if has_n:
+        mb = (L + 7) // 8
+        nmask = np.ascontiguousarray(np.packbits(isn, axis=1, bitorder="little")).reshape(-1)
+        assert nmask.size == n * mb
+        nmask_off = (np.arange(n, dtype=np.int64) * mb).astype(np.uint32)
+    return SeqSet(np.ascontiguousarray(packed), off, np.full(n, L, dtype=np.uint16), nmask, nmask_off)
 
 
 def pack_text_batch(text: np.ndarray, text_off: np.ndarray, lens: np.ndarray, threads: int = 0, with_nmask: bool = True) -> SeqSet:

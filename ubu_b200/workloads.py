@@ -8,7 +8,7 @@ throughput sets; `with_n` sprinkles N for the parity sets.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -114,24 +114,94 @@ def cfg3(n: int = 5_000_000, pool: Optional[int] = None, keep_codes: bool = Fals
                    keep_codes=keep_codes)
 
 
-def cfg4(n: int = 1_000_000, seed: Optional[int] = None) -> Workload:
+def cfg4(n: int = 1_000_000, seed: Optional[int] = None, tie_stress: int = 0) -> Workload:
     """Mixed 50..250 bp reads, indel-rich (3% substitutions, 2% indel events, geometric p=0.3); window = 4x read length
-    rounded up to 64; one window per read."""
+    rounded up to 64; one window per read. Reads of one length are generated together and packed straight into their
+    input-order places (no per-read Python work). tie_stress > 0 turns that many reads (spread over the batch) into the
+    tie-break stress shapes of SURVEY.md section 8d: homopolymers, short tandem repeats, reads that match their window at
+    two offsets with equal score."""
     rng = np.random.Generator(np.random.PCG64(SEEDS["cfg4"] if seed is None else seed))
     lens = rng.integers(50, 251, size=n)
     wlens = ((4 * lens + 63) // 64) * 64
-    reads, wins = [], []
+    rb, wb = (lens + 3) // 4, wlens // 4
+    roff = np.zeros(n, dtype=np.int64); woff = np.zeros(n, dtype=np.int64)
+    if n:
+        np.cumsum(rb[:-1], out=roff[1:]); np.cumsum(wb[:-1], out=woff[1:])
+    rpacked = np.zeros(int(rb.sum()), dtype=np.uint8); wpacked = np.zeros(int(wb.sum()), dtype=np.uint8)
+    stress = np.zeros(n, dtype=np.int8)
+    if tie_stress > 0 and n:
+        stress[np.linspace(0, n - 1, num=min(tie_stress, n)).astype(np.int64)] = 1 + (np.arange(min(tie_stress, n)) % 3)
     cells = 0
     for L in np.unique(lens):
         who = np.nonzero(lens == L)[0]
-        W = int(wlens[who[0]])
-        w = rng.integers(0, 4, size=(who.shape[0], W), dtype=np.uint8)
-        r = _mutate(rng, w, np.arange(who.shape[0]), int(L), 0.03, 0.02, 0.3, max_events=12)
-        for k, t in enumerate(who):
-            reads.append((t, r[k])); wins.append((t, w[k]))
-        cells += who.shape[0] * int(L) * W
-    reads.sort(key=lambda x: x[0]); wins.sort(key=lambda x: x[0])
-    return Workload("cfg4", pack_codes([r for _, r in reads]), pack_codes([w for _, w in wins]), None, cells)
+        L = int(L); W = int(wlens[who[0]]); m = who.shape[0]
+        w = rng.integers(0, 4, size=(m, W), dtype=np.uint8)
+        kind = stress[who]
+        for k in np.nonzero(kind)[0]:                          # few: the stress shapes are built row by row
+            if kind[k] == 1:                                   # homopolymer window (every placement ties)
+                w[k, :] = rng.integers(0, 4)
+            elif kind[k] == 2:                                 # tandem repeat of a 2..6-mer
+                u = rng.integers(0, 4, size=int(rng.integers(2, 7)), dtype=np.uint8)
+                w[k, :] = np.resize(u, W)
+            else:                                              # the read's source stretch occurs twice in the window
+                w[k, W // 2: W // 2 + L + 8] = w[k, 4: 4 + L + 8]
+        r = _mutate(rng, w, np.arange(m), L, 0.03, 0.02, 0.3, max_events=12)
+        for k in np.nonzero(kind == 3)[0]:
+            r[k] = w[k, 8: 8 + L]                              # exact copy: two equal-score placements
+        rp, wp = pack_uniform(r), pack_uniform(w)
+        rpacked[(roff[who][:, None] + np.arange(rp.packed.size // m)[None, :]).reshape(-1)] = rp.packed
+        wpacked[(woff[who][:, None] + np.arange(W // 4)[None, :]).reshape(-1)] = wp.packed
+        cells += m * L * W
+    if max(rpacked.size, wpacked.size) >= 2 ** 32:
+        raise ValueError("batch larger than 4 GiB packed; split it")
+    reads = SeqSet(rpacked, roff.astype(np.uint32), lens.astype(np.uint16), None, None)
+    wins = SeqSet(wpacked, woff.astype(np.uint32), wlens.astype(np.uint16), None, None)
+    return Workload("cfg4", reads, wins, None, cells)
+
+
+def concat(name: str, parts: Sequence[Workload]) -> Workload:
+    """Several workloads as one batch (windows and their indices are offset part by part)."""
+    def cat(sets):
+        base = np.cumsum([0] + [s.packed.size for s in sets[:-1]])
+        off = np.concatenate([(s.off.astype(np.int64) + b) for s, b in zip(sets, base)])
+        if sets and int(base[-1]) + sets[-1].packed.size >= 2 ** 32:
+            raise ValueError("batch larger than 4 GiB packed; split it")
+        return SeqSet(np.concatenate([s.packed for s in sets]), off.astype(np.uint32), np.concatenate([s.len for s in sets]), None, None)
+    assert all(p.reads.nmask is None and p.windows.nmask is None for p in parts)
+    wbase = np.cumsum([0] + [p.windows.count for p in parts[:-1]])
+    idx = None
+    if any(p.pair_ref_idx is not None for p in parts):
+        idx = np.concatenate([(p.pair_ref_idx if p.pair_ref_idx is not None else np.arange(p.n_tasks, dtype=np.uint32)).astype(np.int64) + b
+                              for p, b in zip(parts, wbase)]).astype(np.uint32)
+    return Workload(name, cat([p.reads for p in parts]), cat([p.windows for p in parts]), idx, sum(p.cells for p in parts))
+
+
+def cfg3_sharded(n: int = 5_000_000, shard: int = 500_000, seed: Optional[int] = None, sort_by_window: bool = True, threads: int = 8) -> Workload:
+    """cfg3 generated shard by shard from (seed, shard index), as SURVEY.md section 8d prescribes for the large configs: 150 bp
+    reads vs 2 kb windows, one window per ~5 reads. sort_by_window puts the reads of a window next to each other, which is what
+    coordinate-sorted realignment input looks like (ReAligner.java:237 sorts by coordinate before the per-region work)."""
+    base = SEEDS["cfg3"] if seed is None else seed
+
+    def one(k_lo):
+        k, lo = k_lo
+        m = min(shard, n - lo)
+        w = uniform("cfg3", m, 150, 2000, n_windows=max(m // 5, 1), seed=base + 104729 * k)
+        if sort_by_window and w.pair_ref_idx is not None:
+            order = np.argsort(w.pair_ref_idx, kind="stable")
+            nb = (150 + 3) // 4
+            w = Workload(w.name, SeqSet(np.ascontiguousarray(w.reads.packed.reshape(m, nb)[order]).reshape(-1), w.reads.off, w.reads.len, None, None),
+                         w.windows, np.ascontiguousarray(w.pair_ref_idx[order]), w.cells)
+        return w
+
+    jobs = list(enumerate(range(0, n, shard)))
+    if len(jobs) > 1 and threads > 1:                          # numpy releases the GIL in the heavy parts
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(threads, len(jobs))) as ex:
+            parts = list(ex.map(one, jobs))
+    else:
+        parts = [one(j) for j in jobs]
+    return parts[0] if len(parts) == 1 else concat("cfg3", parts)
 
 
 def with_n(w: Workload, rate: float = 0.01, seed: int = 7) -> Workload:
@@ -139,6 +209,7 @@ def with_n(w: Workload, rate: float = 0.01, seed: int = 7) -> Workload:
     assert w.read_codes is not None and w.window_codes is not None
     rng = np.random.Generator(np.random.PCG64(seed))
     r = w.read_codes.copy(); wn = w.window_codes.copy()
-    r[rng.random(r.shape) < rate] = 4
-    wn[rng.random(wn.shape) < rate] = 4
-    return Workload(w.name + "+N", pack_codes(list(r)), pack_codes(list(wn)), w.pair_ref_idx, w.cells, r, wn)
+    for a in (r, wn):                                          # ~rate of the bases, positions drawn directly (fast on 1e8 bases)
+        flat = a.reshape(-1)
+        flat[rng.integers(0, flat.size, size=rng.binomial(flat.size, rate))] = 4
+    return Workload(w.name + "+N", pack_uniform(r), pack_uniform(wn), w.pair_ref_idx, w.cells, r, wn)
