@@ -56,7 +56,7 @@ int main(int argc, char** argv) {
   // the kernels' epilogue also files every task into a traceback class list (TbPlan, sw_common.cuh)
   uint32_t* d_lists; unsigned int* d_counts; ubu_sw_result* d_res;
   CK(cudaMalloc(&d_lists, sizeof(uint32_t) * (size_t)TB_CLASSES * n)); CK(cudaMalloc(&d_counts, sizeof(unsigned int) * TB_CLASSES)); CK(cudaMalloc(&d_res, sizeof(ubu_sw_result) * n));
-  const TbPlan plan{RectCaps{{96, 160, 256}, {256, 512, 1024}}, d_res, d_lists, d_counts, n};
+  const TbPlan plan{StripCaps{256, 200}, d_res, d_lists, d_counts, n};
   const double cells = (double)n * L * W;
 
   // general kernel (reference for the checksum)

@@ -46,9 +46,9 @@ def main():
     cfgs = {
         "cfg1": lambda: WL.cfg1(10_000),
         "cfg2": lambda: WL.cfg2(int(1_000_000 * a.scale)),
-        "cfg3": lambda: WL.cfg3(int(5_000_000 * a.scale)),
-        "cfg4": lambda: WL.cfg4(int(1_000_000 * a.scale)),
-        "cfg2+N": lambda: WL.with_n(WL.uniform("cfg2", int(200_000 * a.scale) + 1000, 76, 500, seed=5, paired=True, keep_codes=True), 0.005),
+        "cfg3": lambda: WL.cfg3_sharded(int(5_000_000 * a.scale)),
+        "cfg4": lambda: WL.cfg4(int(1_000_000 * a.scale), tie_stress=int(20_000 * a.scale)),
+        "cfg2+N": lambda: WL.with_n(WL.uniform("cfg2", int(1_000_000 * a.scale), 76, 500, seed=5, paired=True, keep_codes=True), 0.005),
     }
     threads = os.cpu_count() or 1
     out = []

@@ -105,30 +105,29 @@ __host__ __device__ __forceinline__ int gap_bound(const Scoring& sc, int i, int 
   return num > 0 ? num / sc.gap_ext : 0;
 }
 
-// ---- traceback classes (sw_tb.cuh, sw_tbrect.cuh). The forward kernels' epilogue sorts every task into one of them ----------
-// 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 diagonals (registers),
-// 4/5/6: wide bands, systolic rectangle fill with rows <= rows[c] and width <= wcap[c], 7: scalar last resort
-constexpr int TB_CLASSES = 8;
-struct RectCaps { int rows[3]; int wcap[3]; };
+// ---- traceback classes (sw_tb.cuh, sw_tbstrip.cuh). The forward kernels' epilogue sorts every task into one of them ----------
+// 0: no gap possible (Gb == 0, pure diagonal scan), 1/2/3: band <= 8/16/32 diagonals (band row in registers),
+// 4..8: wide bands by width (<= 48 / 64 / 88 / 120 / bw_cap diagonals): row strips in registers, one thread per pair
+// (sw_tbstrip.cuh; the width classes only group similar tasks into the same warps), 9: scalar last resort
+constexpr int TB_CLASSES = 10;
+constexpr int TB_STRIP_FIRST = 4, TB_STRIP_CLASSES = 5, TB_CLASS_SCALAR = 9;
+struct StripCaps { int rows_cap, bw_cap; };         // what the strip kernel's scratch of this batch was sized for (0 = strips off)
 struct TbPlan {                        // where the epilogue puts its verdicts
-  RectCaps caps;
+  StripCaps caps;
   ubu_sw_result* res;                  // unaligned tasks (score <= 0) get their final record right away
   uint32_t* lists;                     // [TB_CLASSES][n_slots] task lists
   unsigned int* counts;                // [TB_CLASSES]
   uint32_t n_slots;
 };
-__device__ __forceinline__ int tb_class_of(const Scoring& sc, const FwdOut& f, const RectCaps& caps) {
+__device__ __forceinline__ int tb_class_of(const Scoring& sc, const FwdOut& f, const StripCaps& caps) {
   const int gb = gap_bound(sc, f.i_hi, f.score);
   const int bw = (f.i_hi - f.i_lo) + 2 * gb + 1;
   if (gb == 0) return 0;
   if (bw <= 8) return 1;
   if (bw <= 16) return 2;
   if (bw <= 32) return 3;
-  const int clo = max(1, 1 + f.je - f.i_hi - gb), w = f.je - clo + 1;             // rectangle of sw_tbrect.cuh
-  int cls = 7;
-#pragma unroll
-  for (int c = 2; c >= 0; --c) if (f.i_hi <= caps.rows[c] && w <= caps.wcap[c]) cls = 4 + c;
-  return cls;
+  if (bw > caps.bw_cap || f.i_hi > caps.rows_cap) return TB_CLASS_SCALAR;
+  return bw <= 48 ? 4 : bw <= 64 ? 5 : bw <= 88 ? 6 : bw <= 120 ? 7 : 8;
 }
 
 }  // namespace ubu

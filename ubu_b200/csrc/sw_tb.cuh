@@ -24,7 +24,7 @@
 // Kernels: the forward kernels' epilogue sorts tasks into band-width classes (tb_class_of, sw_common.cuh); tb_diag_kernel
 // handles the gap-free class;
 // tb_fill_reg_kernel<BW> keeps the band row in registers (BW = 8, 16 or 32 diagonals); wider bands go to
-// tb_rect_kernel (sw_tbrect.cuh); tb_wide_kernel (scalar, global scratch, direction bits) is the last
+// tb_strip_kernel (sw_tbstrip.cuh); tb_wide_kernel (scalar, global scratch, direction bits) is the last
 // resort (extreme scoring parameters / very long windows only).
 #pragma once
 #include "sw_common.cuh"

@@ -5,7 +5,7 @@
 #include "sw_fwd16.cuh"
 #include "sw_fwd16s.cuh"
 #include "sw_tb.cuh"
-#include "sw_tbrect.cuh"
+#include "sw_tbstrip.cuh"
 #include "sw_post.cuh"
 
 #include <algorithm>
@@ -35,12 +35,10 @@ constexpr int kNumCfgs = (int)(sizeof(kFwdCfgs) / sizeof(kFwdCfgs[0]));
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
 constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
-#ifndef UBU_TBR_MIN_BLOCKS
-#define UBU_TBR_MIN_BLOCKS 8
-#endif
-constexpr int TBR_THREADS = 64, TBR_GRID_PER_SM = UBU_TBR_MIN_BLOCKS;     // wide bands: systolic rectangle fill, three (rows, G, K) classes
-struct RectCfg { int rows, G, K; };
-const RectCfg kRectCfgs[3] = {{96, 8, 12}, {160, 8, 20}, {256, 16, 16}};
+constexpr int TBS_GRID_PER_SM = UBU_TBS_MIN_BLOCKS;      // wide bands: row strips in registers, one thread per task pair (sw_tbstrip.cuh)
+constexpr int kStripBwCap = 200;                         // widest band the strip kernel takes (its walk keeps <= bw + 8 CIGAR runs)
+constexpr size_t kStripScratchBudget = (size_t)6 << 30;  // per pipeline slot; fewer CTAs are launched when a batch's worst case would need more
+constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, strip work counter
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
 constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
 
@@ -74,7 +72,7 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kAux = 5;
+constexpr int kAux = 4;
 constexpr int kMaxSlots = 8;                          // depth of the H2D / compute / D2H pipeline (ubu_sw_create)
 struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint32_t n_tasks; bool shared_win = false; };   // shared_win: both tasks of every pair sweep the same window   // selectors go to global scratch when they do not fit shared memory
 
@@ -88,15 +86,15 @@ struct Slot {
   DevBuf<uint16_t> d_rlen, d_wlen;
   DevBuf<FwdOut> d_fwd;
   DevBuf<ubu_sw_result> d_res;
-  DevBuf<unsigned int> d_ctr;            // [0..7] class counts, [8] cigar cursor, [9] error flags
-  DevBuf<uint32_t> d_hstore;             // packed H of every band cell: [BW=8 | BW=16 | BW=32 | shared-memory band] regions
-  size_t h_off[6] = {0, 0, 0, 0, 0, 0};   // band 8 | 16 | 32 | rectangle classes 0, 1, 2
-  size_t ops_off[3] = {0, 0, 0};
-  RectCaps caps{{0, 0, 0}, {0, 0, 0}};
-  bool rect_on[3] = {false, false, false};
+  DevBuf<unsigned int> d_ctr;            // [0..TB_CLASSES) class counts, then CTR_CIG, CTR_ERR, CTR_WORK
+  DevBuf<uint32_t> d_hstore;             // packed H of every band cell of the register-band kernels: [BW=8 | BW=16 | BW=32] regions
+  size_t h_off[3] = {0, 0, 0};
+  int tb_grid = 1;                       // CTAs of the register-band kernels (sized by the batch)
+  StripCaps caps{0, 0};
+  DevBuf<unsigned char> d_strip;         // H store + boundary arrays of the strip kernel's warps
+  size_t strip_bnd_off = 0; int strip_grid = 0, strip_bytes = 1;
   int tbw_grid = 1;
   bool pre_queued = false; size_t pre_words = 0;   // early device->host copies queued by submit()
-  DevBuf<uint32_t> d_ops;                // CIGAR run scratch of the shared-memory-band traceback
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
   DevBuf<unsigned char> d_gsel;          // per-column selectors of forward launches with very long windows
   PinBuf<uint32_t> h_order;
@@ -265,33 +263,18 @@ cudaError_t launch_fwd(const FwdLaunch& L, const DevSeqs& reads, const DevSeqs& 
   }
 }
 
-template <int G, int K, bool HAS_N, bool DEF>
-cudaError_t launch_rect_t(int grid, const TbArgs& a, const uint32_t* list, const unsigned int* count, uint32_t* scratch, uint32_t* ops,
-                          int wcap, cudaStream_t st) {
-  constexpr int GP = TBR_THREADS / G;
-  const int sel_stride = ((wcap + 2 * G + 15) / 16) * 16;
-  const size_t smem = (size_t)GP * sel_stride * (HAS_N ? 4u : 2u);
-  auto kern = tb_rect_kernel<G, K, HAS_N, DEF, TBR_THREADS>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return e;
+cudaError_t launch_strip(bool has_n, bool def, int bytes, int grid, const TbArgs& a, const StripArgs& sa, cudaStream_t st) {
+  switch ((has_n ? 1 : 0) + (def ? 2 : 0) + (bytes == 2 ? 4 : 0)) {
+    case 0: tb_strip_kernel<false, false, 1><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 1: tb_strip_kernel<true, false, 1><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 2: tb_strip_kernel<false, true, 1><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 3: tb_strip_kernel<true, true, 1><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 4: tb_strip_kernel<false, false, 2><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 5: tb_strip_kernel<true, false, 2><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    case 6: tb_strip_kernel<false, true, 2><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
+    default: tb_strip_kernel<true, true, 2><<<grid, TBS_THREADS, 0, st>>>(a, sa); break;
   }
-  kern<<<grid, TBR_THREADS, smem, st>>>(a, list, count, scratch, ops, wcap, sel_stride);
   return cudaGetLastError();
-}
-
-cudaError_t launch_rect(int c, bool has_n, bool def, int grid, const TbArgs& a, const uint32_t* list, const unsigned int* count,
-                        uint32_t* scratch, uint32_t* ops, int wcap, cudaStream_t st) {
-  switch (c * 4 + (has_n ? 1 : 0) + (def ? 2 : 0)) {
-#define R(i, g, k) \
-    case i * 4: return launch_rect_t<g, k, false, false>(grid, a, list, count, scratch, ops, wcap, st); \
-    case i * 4 + 1: return launch_rect_t<g, k, true, false>(grid, a, list, count, scratch, ops, wcap, st); \
-    case i * 4 + 2: return launch_rect_t<g, k, false, true>(grid, a, list, count, scratch, ops, wcap, st); \
-    case i * 4 + 3: return launch_rect_t<g, k, true, true>(grid, a, list, count, scratch, ops, wcap, st);
-    R(0, 8, 12) R(1, 8, 20) R(2, 16, 16)
-#undef R
-    default: return cudaErrorInvalidValue;
-  }
 }
 
 bool params_ok(const ubu_sw_params& p) {
@@ -550,29 +533,30 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   {
     const int gbmax = gap_bound(h->sc, max_rows, 1);
     s.bw_cap = std::min(kMaxK + 2 * gbmax + 1, max_rows + 65535);
-    const size_t reg_threads = (size_t)h->sm_count * TB_GRID_PER_SM * TB_THREADS;
+    // grids are sized by the batch (a small batch must not pin the scratch of a full one)
+    const size_t pair_ctas = ((size_t)(n + 1) / 2 + TB_THREADS - 1) / TB_THREADS;
+    s.tb_grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->sm_count * TB_GRID_PER_SM, pair_ctas));
+    const size_t reg_threads = (size_t)s.tb_grid * TB_THREADS;
     s.h_off[0] = 0;
     s.h_off[1] = s.h_off[0] + reg_threads * (size_t)max_rows * 8;
     s.h_off[2] = s.h_off[1] + reg_threads * (size_t)max_rows * 16;
-    s.h_off[3] = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
-    size_t hwords = s.h_off[3], opwords = 0;
-    // wide bands: rectangle classes by read rows; width cap = rows + the largest gap budget those rows allow
-    for (int c = 0; c < 3; ++c) {
-      const RectCfg& rc_ = kRectCfgs[c];
-      const int rows = std::min(rc_.rows, max_rows);
-      int wcap = rows + gap_bound(h->sc, rows, 1);
-      wcap = std::min(((wcap + 15) / 16) * 16, 4096);
-      s.rect_on[c] = (c == 0 || max_rows > kRectCfgs[c - 1].rows) && s.bw_cap > 32;
-      s.caps.rows[c] = s.rect_on[c] ? rc_.rows : 0; s.caps.wcap[c] = s.rect_on[c] ? wcap : 0;
-      const size_t groups = (size_t)h->sm_count * TBR_GRID_PER_SM * (TBR_THREADS / rc_.G);
-      s.h_off[3 + c] = hwords; s.ops_off[c] = opwords;
-      if (s.rect_on[c]) {
-        hwords += groups * (size_t)wcap * (size_t)(rc_.G * rc_.K);
-        opwords += (size_t)h->sm_count * TBR_GRID_PER_SM * TBR_THREADS * (size_t)(2 * wcap + 16);
-      }
+    const size_t hwords = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
+    // wide bands: strip kernel. One byte per stored H when no score of the batch can exceed 255, else two.
+    s.caps.rows_cap = 0; s.caps.bw_cap = 0; s.strip_grid = 0;
+    if (s.bw_cap > 32) {
+      s.caps.rows_cap = max_rows; s.caps.bw_cap = std::min(s.bw_cap, kStripBwCap);
+      s.strip_bytes = (h->sc.match * max_rows <= 255) ? 1 : 2;
+      const size_t per_warp_h = tbs_hstore_bytes_per_warp(s.caps.rows_cap, s.caps.bw_cap, s.strip_bytes),
+                   per_warp_b = tbs_boundary_bytes_per_warp(s.caps.rows_cap, s.caps.bw_cap);
+      const size_t per_cta = (per_warp_h + per_warp_b) * (TBS_THREADS / 32);
+      const size_t strip_ctas = ((size_t)(n + 1) / 2 + TBS_THREADS - 1) / TBS_THREADS;
+      size_t grid = std::min<size_t>((size_t)h->sm_count * TBS_GRID_PER_SM, strip_ctas);
+      grid = std::max<size_t>(1, std::min<size_t>(grid, kStripScratchBudget / per_cta));
+      s.strip_grid = (int)grid;
+      s.strip_bnd_off = grid * (TBS_THREADS / 32) * per_warp_h;
+      CU(h, s.d_strip.reserve(s.strip_bnd_off + grid * (TBS_THREADS / 32) * per_warp_b + 256));
     }
     CU(h, s.d_hstore.reserve(hwords));
-    CU(h, s.d_ops.reserve(opwords + 8));
     {
       // the scalar last resort only sees bands no other class takes (extreme scoring / very long windows): its band can be
       // as wide as the whole window, so its scratch is capped at 2 GB by running fewer CTAs
@@ -629,7 +613,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
 
   TbArgs a;
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
-  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + 8; a.err_flag = s.d_ctr.p + 9;
+  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + CTR_CIG; a.err_flag = s.d_ctr.p + CTR_ERR;
   const int max_rows = std::max(s.lmax, 1);
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
@@ -639,7 +623,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
   CU(h, cudaGetLastError()); ++s.n_launches;
   {
-    const int grid = h->sm_count * TB_GRID_PER_SM;
+    const int grid = s.tb_grid;
     const size_t selsz = s.any_n ? 4 : 2;
     const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
                  sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
@@ -667,15 +651,17 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     }
     s.n_launches += 3;
   }
-  for (int c = 0; c < 3; ++c) {                       // wide bands: rectangle classes, each on its own stream
-    if (!s.rect_on[c]) continue;
+  if (s.strip_grid > 0) {                             // wide bands: one launch serves all strip classes, widest first
     const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
-    CU(h, launch_rect(c, s.any_n, def, h->sm_count * TBR_GRID_PER_SM, a, s.d_lists.p + (4 + c) * NS, s.d_ctr.p + 4 + c,
-                      s.d_hstore.p + s.h_off[3 + c], s.d_ops.p + s.ops_off[c], s.caps.wcap[c], s.aux[2 + c]));
+    StripArgs sa;
+    sa.lists = s.d_lists.p; sa.counts = s.d_ctr.p; sa.work = s.d_ctr.p + CTR_WORK; sa.n_slots = s.n_slots;
+    sa.hstore = s.d_strip.p; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + s.strip_bnd_off);
+    sa.rows_cap = s.caps.rows_cap; sa.bw_cap = s.caps.bw_cap;
+    CU(h, launch_strip(s.any_n, def, s.strip_bytes, s.strip_grid, a, sa, s.aux[2]));
     ++s.n_launches;
   }
-  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, s.aux[4]>>>(a, s.d_lists.p + 7 * NS, s.d_ctr.p + 7,
-                                                                            s.d_wide.p, max_rows, s.bw_cap);
+  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, s.aux[3]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
+                                                          s.d_wide.p, max_rows, s.bw_cap);
   CU(h, cudaGetLastError()); ++s.n_launches;
   for (int k = 0; k < kAux; ++k) {                    // join
     CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
@@ -709,7 +695,7 @@ int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size
   if (s.pre_queued) {                  // fast path of wait(): everything may already be on its way
     s.pre_queued = false;
     CU(h, cudaStreamSynchronize(st));
-    const unsigned int need = s.h_ctr.p[8], err = s.h_ctr.p[9];
+    const unsigned int need = s.h_ctr.p[CTR_CIG], err = s.h_ctr.p[CTR_ERR];
     if (!err && need <= pool_cap && (need == 0 || pool)) {
       if (need > s.pre_words) {
         CU(h, cudaMemcpyAsync(pool + s.pre_words, s.d_cig.p + s.pre_words, sizeof(uint32_t) * (need - s.pre_words), cudaMemcpyDeviceToHost, st));
@@ -722,7 +708,7 @@ int do_fetch(ubu_sw_handle* h, Slot& s, ubu_sw_result* out, uint32_t* pool, size
   for (int attempt = 0;; ++attempt) {
     CU(h, cudaMemcpyAsync(s.h_ctr.p, s.d_ctr.p, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
-    const unsigned int need = s.h_ctr.p[8], err = s.h_ctr.p[9];
+    const unsigned int need = s.h_ctr.p[CTR_CIG], err = s.h_ctr.p[CTR_ERR];
     if (err & 2u) { h->last_error = "internal: traceback left its band (please report)"; return UBU_SW_ERR_CUDA; }
     if (err & 1u) {                    // device CIGAR pool was too small: grow it and redo the device work once
       if (attempt) { h->last_error = "internal: CIGAR pool overflow after regrow"; return UBU_SW_ERR_CUDA; }
@@ -810,7 +796,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
     s.d_roff.release(); s.d_rnoff.release(); s.d_woff.release(); s.d_wnoff.release(); s.d_idx.release();
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
-    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_ops.release(); s.d_wide.release(); s.d_gsel.release();
+    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_strip.release(); s.d_wide.release(); s.d_gsel.release();
     s.h_order.release(); s.h_ctr.release();
     s.h_pool.release();
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
