@@ -122,6 +122,25 @@ int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]);
 /* Number of kernel launches issued by the last run() on the slot. */
 int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot);
 
+/* ---- one process, several GPUs (BASELINE.json configs[4]) -------------------------------------------
+ * The reference hands parallelism to `bwa -t numThreads` (Aligner.java:19,49) and treats its inputs as independent work
+ * (ReAligner.java:180-184,199-200). Reads shard trivially: there is no collective and no peer traffic. The driver owns one
+ * handle and one host thread per device; the batch is cut into input-order chunks of `chunk_reads` reads, chunk c runs on
+ * device c mod N through that handle's slots. Nothing is merged on the host afterwards: every chunk owns a slice of the
+ * caller's CIGAR pool proportional to its reads (slice c starts at cigar_pool_cap * first_read(c) / reads), the kernels
+ * write final cigar_off values, and records and ops are copied by the GPUs straight into their input-order places.
+ * Consequences for the caller: out[k] / cigar slices are in input order exactly as with ubu_sw_align_batch, but the pool is
+ * not dense (*cigar_pool_used = its high-water mark); when a slice is too small the call returns UBU_SW_ERR_CIGAR_POOL and
+ * *cigar_pool_used = a capacity with which every slice fits. Pinned buffers (ubu_sw_host_alloc) make the copies asynchronous. */
+typedef struct ubu_sw_multi ubu_sw_multi;
+/* devices == NULL: the first n_devices visible devices (n_devices <= 0: all). slots as in ubu_sw_create; chunk_reads 0 -> 65536. */
+int ubu_sw_multi_create(const ubu_sw_params* params, const int* devices, int n_devices, int slots, uint32_t chunk_reads, ubu_sw_multi** out);
+void ubu_sw_multi_destroy(ubu_sw_multi* m);
+int ubu_sw_multi_device_count(const ubu_sw_multi* m);
+const char* ubu_sw_multi_last_error(ubu_sw_multi* m);
+int ubu_sw_multi_align(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                       ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);
+
 /* ---- the steps right behind the aligner; bug-compatible with the Java they replace ---- */
 
 /* Long reference sequences (chromosomes), same 2-bit code + N plane; replaces the per-chromosome StringBuffer that
@@ -187,6 +206,12 @@ typedef struct {
 /* Formats on `threads` host threads (0 = all cores) and writes the blocks to file descriptor fd in order (fd < 0: format only). */
 int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* cigar_pool, uint32_t n,
                      const ubu_sw_sam_names* names, int threads, uint64_t* bytes_written);
+/* ubu_sw_multi_align followed by the SAM text of the batch (the ordered host merge of BASELINE.json configs[4]): finished chunks are
+ * released in input order, formatted on sam_threads helper threads (0 = all cores) and written to fd (fd < 0: format only) while
+ * later chunks are still on the GPUs. */
+int ubu_sw_multi_align_sam(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                           ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used,
+                           int fd, const ubu_sw_sam_names* names, int sam_threads, uint64_t* bytes_written);
 /* ReverseComplementor.java:38-62: A<->T, C<->G, every other byte unchanged. */
 void ubu_sw_revcomp(const char* in, size_t n, char* out);
 /* BAM-encoded ops -> "76M" style text; returns chars written (excluding NUL), "*" for n == 0. */

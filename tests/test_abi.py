@@ -60,6 +60,15 @@ def test_no_cpu_fallback_product_path_fails_loudly():
     with pytest.raises(U.UbuSwError) as e:
         U.SwAligner()
     assert e.value.status == N.ERR_NO_DEVICE
+    from ubu_b200 import multi as M
+
+    with pytest.raises(U.UbuSwError) as e:                      # the multi-GPU driver has no CPU path either
+        M.MultiAligner()
+    assert e.value.status == N.ERR_NO_DEVICE
+    m = C.c_void_p()
+    assert N.lib().ubu_sw_multi_create(None, None, 0, 0, 0, None) == N.ERR_ARG
+    assert N.lib().ubu_sw_multi_align(None, None, None, None, None, None, 0, None) == N.ERR_ARG
+    assert N.lib().ubu_sw_multi_device_count(None) == 0
 
 
 def test_pack_helper_matches_numpy_packer_and_reference_convention():

@@ -506,3 +506,65 @@ def test_mixed_batch_pairs_window_sharing_neighbours(aligner, monkeypatch):
     monkeypatch.delenv("UBU_NO_SHARED_WIN")
     for f in FIELDS + ("cigar_n", "flags"):
         assert np.array_equal(got.results[f], want.results[f]), f
+
+
+def test_multi_gpu_driver_equals_one_call(aligner):
+    """ubu_sw_multi_align (C++ driver inside the library: a host thread + handle per GPU, chunk c -> GPU c mod N, per-chunk slices of
+    the caller's CIGAR pool, no host merge pass) on all visible GPUs returns what one ubu_sw_align_batch call returns: records in
+    input order, CIGARs equal; windows shared across chunk borders, ragged reads, N; then a scattered (non-compact) layout; then
+    SAM text equal to ubu_sw_sam_write's."""
+    import os
+    import tempfile
+
+    from ubu_b200 import multi as M
+
+    rng = np.random.default_rng(4)
+    base = WL.uniform("mg", 30_011, 100, 700, n_windows=4_000, seed=91, sub_rate=0.03, indel_rate=0.01, keep_codes=True)
+    order = np.argsort(base.pair_ref_idx, kind="stable")
+    codes = base.read_codes[order]
+    codes[rng.random(codes.shape) < 0.002] = 4
+    reads = U.pack_codes([c[: int(rng.integers(60, 101))] for c in codes])
+    idx = base.pair_ref_idx[order]
+    one = aligner.align(reads, base.windows, idx)
+    with M.MultiAligner(chunk=2_500, slots=3) as m:
+        assert m.n_devices >= 1
+        for _ in range(2):
+            got = m.align(reads, base.windows, idx)
+            for f in FIELDS + ("cigar_n", "flags"):
+                assert np.array_equal(got.results[f], one.results[f]), f
+            assert all(got.cigar(k) == one.cigar(k) for k in range(0, len(one), 7))
+        # scattered reads (window indices all over the set): chunks are not compact, every chunk uploads the whole window set
+        perm = rng.permutation(reads.count)
+        reads_s = U.pack_codes([reads.codes(int(k)) for k in perm])
+        got = m.align(reads_s, base.windows, idx[perm])
+        for f in FIELDS + ("cigar_n", "flags"):
+            assert np.array_equal(got.results[f], one.results[f][perm]), f
+        assert all(got.cigar(k) == one.cigar(int(perm[k])) for k in range(0, len(one), 11))
+        # SAM text behind the merge == the single-call SAM writer on the single-call results
+        with tempfile.TemporaryDirectory() as td:
+            p1, p2 = os.path.join(td, "multi.sam"), os.path.join(td, "one.sam")
+            fd = os.open(p1, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+            try:
+                got = m.align(reads, base.windows, idx, sam_fd=fd, sam_threads=3)
+            finally:
+                os.close(fd)
+            fd = os.open(p2, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+            try:
+                U.write_sam(fd, reads, one, idx)
+            finally:
+                os.close(fd)
+            assert open(p1, "rb").read() == open(p2, "rb").read() and m.last_sam_bytes == os.path.getsize(p2)
+    # a pool that is too small: status + a capacity that works
+    with M.MultiAligner(chunk=2_500) as m:
+        rs, ws = reads.as_struct(), base.windows.as_struct()
+        import ctypes as C
+        from ubu_b200 import _native as N
+        res = np.zeros(reads.count, dtype=U.RESULT_DTYPE); pool = np.zeros(reads.count // 2, dtype=np.uint32); used = C.c_size_t(0)
+        ix = np.ascontiguousarray(idx, dtype=np.uint32)
+        rc = N.lib().ubu_sw_multi_align(m._m, C.byref(rs), C.byref(ws), ix.ctypes.data, res.ctypes.data, pool.ctypes.data, pool.shape[0], C.byref(used))
+        assert rc == N.ERR_CIGAR_POOL and used.value > pool.shape[0]
+        pool = np.zeros(used.value, dtype=np.uint32)
+        rc = N.lib().ubu_sw_multi_align(m._m, C.byref(rs), C.byref(ws), ix.ctypes.data, res.ctypes.data, pool.ctypes.data, pool.shape[0], C.byref(used))
+        assert rc == 0
+        for f in FIELDS + ("cigar_n", "flags"):
+            assert np.array_equal(res[f], one.results[f]), f

@@ -62,6 +62,24 @@ __device__ __forceinline__ uint32_t load16(const uint8_t* __restrict__ seq, int 
   const uint32_t v = __funnelshift_r(w[0], w[1], sh);
   return adj >= 16 ? 0u : (v << (2 * adj));
 }
+// load16 in two halves, for software prefetch: issue() puts the two 32-bit loads in flight, finish() (called a block of work
+// later) shifts the 16 bases out. Same result as load16(seq, start).
+struct Load16 {
+  uint32_t w0, w1, sh; int adj;
+  __device__ __forceinline__ void issue(const uint8_t* __restrict__ seq, int start, bool on) {
+    adj = start < 0 ? -start : 0;
+    const int s0 = start + adj;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(seq) + (uintptr_t)(s0 >> 2);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+    sh = (uint32_t)(addr & 3u) * 8u + (uint32_t)(s0 & 3) * 2u;
+    w0 = 0u; w1 = 0u;
+    if (on) { w0 = w[0]; w1 = w[1]; }
+  }
+  __device__ __forceinline__ uint32_t finish() const {
+    const uint32_t v = __funnelshift_r(w0, w1, sh);
+    return adj >= 16 ? 0u : (v << (2 * adj));
+  }
+};
 // 16 consecutive N-plane bits (bit `start` in bit 0); same conventions.
 __device__ __forceinline__ uint32_t load16n(const uint8_t* __restrict__ nm, int start) {
   const int adj = start < 0 ? -start : 0;

@@ -45,6 +45,8 @@ struct TbArgs {
   unsigned int cig_cap;
   unsigned int* cig_cursor;
   unsigned int* err_flag;        // bit 0: pool overflow, bit 1: internal inconsistency
+  unsigned int cig_base;         // added to every record's cigar_off: where this batch's ops will sit in the CALLER's pool
+                                 // (the multi-GPU driver gives every chunk its own slice, so nothing is rebased on the host)
 };
 
 // Band geometry of one task (SPEC.md section 7).
@@ -93,7 +95,7 @@ __device__ __forceinline__ void emit_result(const TbArgs& a, uint32_t task, cons
   r.score = S; r.ref_start = ref_start; r.ref_end = je; r.q_start = q_start; r.q_end = ie; r.edit_distance = edits;
   r.flags = 0; r.cigar_n = (uint16_t)o.n;
   const unsigned off = atomicAdd(a.cig_cursor, (unsigned)o.n);
-  r.cigar_off = off;
+  r.cigar_off = off + a.cig_base;
   if (off + (unsigned)o.n <= a.cig_cap) {
     for (int k = 0; k < o.n; ++k) a.cig_pool[off + k] = o.ops[o.n - 1 - k];
   } else {
@@ -340,7 +342,7 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
     unsigned base = 0u;
     if (cg_.thread_rank() == cg_.size() - 1) base = atomicAdd(a.cig_cursor, pre + (unsigned)no);
     const unsigned off = cg_.shfl(base, cg_.size() - 1) + pre;
-    r.cigar_off = off;
+    r.cigar_off = off + a.cig_base;
     if (off + (unsigned)no <= a.cig_cap) { for (int k = 0; k < no; ++k) a.cig_pool[off + k] = ops[k]; }
     else atomicOr(a.err_flag, 1u);
     a.res[task] = r;

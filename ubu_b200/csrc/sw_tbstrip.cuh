@@ -73,6 +73,10 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
   uint2* bnd = sa.boundary + (size_t)warp_global * (tbs_boundary_bytes_per_warp(sa.rows_cap, sa.bw_cap) / 8u) + lane;
   uint4* hlane = reinterpret_cast<uint4*>(hwarp) + lane;         // chunk (step, c) of this lane at hlane[(step * CHUNKS + c) * 32]
   uint32_t opbuf[2 * 96 + 16];                                   // CIGAR runs of one walk (local memory; <= 2 * gaps + 3 runs)
+  // boundary staging: per warp a double buffer of 16 steps x 32 lanes x 8 bytes
+  __shared__ __align__(16) uint2 sm_all[(TBS_THREADS / 32) * 2 * 16 * 32];
+  const uint2* sm_mine = sm_all + (threadIdx.x >> 5) * (2 * 16 * 32) + lane;
+  const uint32_t sm_bnd = (uint32_t)__cvta_generic_to_shared(sm_mine);
 
   // units of 32 pairs, widest class first
   unsigned int cnt[TB_STRIP_CLASSES], unit_end[TB_STRIP_CLASSES];
@@ -118,15 +122,23 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
     const int clip = ok ? max(ga.je - ga.c0, gb.je - gb.c0) : 0;
 
     int p_prev = 0;
+    uint32_t corner = NEG_OE;                                    // H[last row of the strip above][column left of step 0] - oe
+    uint32_t qa_n = 0u, qb_n = 0u, na_n = 0u, nb_n = 0u;         // read words of the next strip, fetched a strip ahead
+    auto load_rows = [&](int r) {
+      const int ia = ga.i_first - 1 + r * K, ib = gb.i_first - 1 + r * K;      // 0-based read position of row 0 of the strip
+      qa_n = (ok && ia < va.L) ? load16(va.q, ia) : 0u; qb_n = (ok && ib < vb.L) ? load16(vb.q, ib) : 0u;
+      if (HAS_N) { na_n = (ok && va.qn && ia < va.L) ? load16n(va.qn, ia) : 0u; nb_n = (ok && vb.qn && ib < vb.L) ? load16n(vb.qn, ib) : 0u; }
+    };
+    load_rows(0);
     for (int r = 0; r < nstrips; ++r) {
       const int psteps = min(K + bw - 1, clip - r * K);
+      const uint32_t qa = qa_n, qb = qb_n, na = na_n, nb = nb_n;
+      if (r + 1 < nstrips) load_rows(r + 1);
       if (psteps <= 0) { p_prev = 0; continue; }
       // ---- row profiles of the strip (16 rows = one load16 per task) ----
       uint32_t profA[K], profB[K];
       {
-        const int ia = ga.i_first - 1 + r * K, ib = gb.i_first - 1 + r * K;      // 0-based read position of row 0 of the strip
-        const uint32_t qa = ia < va.L ? load16(va.q, ia) : 0u, qb = ib < vb.L ? load16(vb.q, ib) : 0u;
-        const uint32_t na = (HAS_N && va.qn && ia < va.L) ? load16n(va.qn, ia) : 0u, nb = (HAS_N && vb.qn && ib < vb.L) ? load16n(vb.qn, ib) : 0u;
+        const int ia = ga.i_first - 1 + r * K, ib = gb.i_first - 1 + r * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           profA[k] = profile_of((qa >> (2 * k)) & 3u, (na >> k) & 1u, ia + k < va.L, MM4, MX, N4);
@@ -139,58 +151,81 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
       const int ca0 = ga.c0 + r * K, cb0 = gb.c0 + r * K;       // 0-based window column of step 0
       uint2* brow = bnd + (size_t)(r * K) * 32;                  // boundary slot of step p: brow[p * 32]
       const int top_valid = (r > 0) ? p_prev - K : 0;            // steps p < top_valid have a real strip above them
-      uint32_t hoe_up_prev = NEG_OE;
-      if (r > 0 && p_prev >= K) hoe_up_prev = brow[-32].x;       // H[row above][column left of step 0] - oe
-      uint2 top = (0 < top_valid) ? brow[0] : make_uint2(NEG_OE, NEG_OE);
-      uint32_t wa = 0u, wb = 0u, fa_ = 0u, fb_ = 0u;
+      uint32_t hoe_up_prev = (r > 0 && p_prev >= K) ? corner : NEG_OE;
       uint4* hstrip = hlane + (size_t)(r * pw) * CHUNKS * 32;
+      // Everything a block of 16 steps reads from memory is requested one block ahead: the boundary values by cp.async into
+      // this warp's double buffer in shared memory (no registers held while they fly), the window words into registers.
+      Load16 la, lb;                                             // window words of the next block, in flight
+      uint32_t fa_n = 0u, fb_n = 0u;
+      auto prefetch = [&](int blk) {
+        const int p0 = blk * 16;
+        if (p0 < top_valid) {
+          const uint32_t dst = sm_bnd + (uint32_t)((blk & 1) * 16 * 32 * 8);
+          const uint2* src = brow + (size_t)p0 * 32;
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + (uint32_t)(u * 32 * 8)), "l"(src + (size_t)u * 32) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int ca = ca0 + p0, cb = cb0 + p0;
+        la.issue(va.r, ca, ca < va.W && ca + 16 > 0); lb.issue(vb.r, cb, cb < vb.W && cb + 16 > 0);
+        if (HAS_N) { fa_n = (va.rn && ca < va.W && ca + 16 > 0) ? load16n(va.rn, ca) : 0u; fb_n = (vb.rn && cb < vb.W && cb + 16 > 0) ? load16n(vb.rn, cb) : 0u; }
+      };
+      prefetch(0);
+      const int nblk = (psteps + 15) / 16;
 #pragma unroll 1
-      for (int p = 0; p < psteps; ++p) {
-        const uint2 top_next = (p + 1 < top_valid) ? brow[(p + 1) * 32] : make_uint2(NEG_OE, NEG_OE);      // one step ahead
-        const int ca = ca0 + p, cb = cb0 + p;
-        if ((p & 15) == 0) {
-          wa = (ca < va.W && ca + 16 > 0) ? load16(va.r, ca) : 0u; wb = (cb < vb.W && cb + 16 > 0) ? load16(vb.r, cb) : 0u;
-          if (HAS_N) { fa_ = (va.rn && ca < va.W && ca + 16 > 0) ? load16n(va.rn, ca) : 0u; fb_ = (vb.rn && cb < vb.W && cb + 16 > 0) ? load16n(vb.rn, cb) : 0u; }
-        }
-        const int u = p & 15;
-        uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;                 // outside the window: sign-replicate selectors (score <= 0 after bias)
-        if (ca >= 0 && ca < va.W) { lo = ((wa >> (2 * u)) & 3u) * 0x11u + 0x80u; if (HAS_N && ((fa_ >> u) & 1u)) nf |= 0x00800000u; }
-        if (cb >= 0 && cb < vb.W) { hi = ((wb >> (2 * u)) & 3u) * 0x11u + 0xC4u; if (HAS_N && ((fb_ >> u) & 1u)) nf |= 0x80000000u; }
-        const uint32_t selv = lo | (hi << 8);
-        uint32_t isn = 0u;
-        if (HAS_N) isn = prmt(nf, 0u, 0xBBAAu);
-        uint32_t hd = hoe_up_prev;
-        hoe_up_prev = top.x;
-        uint32_t F = top.y;
-        uint32_t hv[K];
+      for (int blk = 0; blk < nblk; ++blk) {
+        const uint32_t wa = la.finish(), wb = lb.finish(), fa_ = fa_n, fb_ = fb_n;
+        if (blk + 1 < nblk) prefetch(blk + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this block's boundary values have landed
+        const uint2* sblk = sm_mine + (blk & 1) * 16 * 32;
+        const int pend = min(16, psteps - blk * 16);
+#pragma unroll 1
+        for (int u = 0; u < pend; ++u) {
+          const int p = blk * 16 + u;
+          uint2 top = sblk[u * 32];
+          if (p >= top_valid) top = make_uint2(NEG_OE, NEG_OE);
+          const int ca = ca0 + p, cb = cb0 + p;
+          uint32_t lo = 0x88u, hi = 0xCCu, nf = 0u;               // outside the window: sign-replicate selectors (score <= 0 after bias)
+          if (ca >= 0 && ca < va.W) { lo = ((wa >> (2 * u)) & 3u) * 0x11u + 0x80u; if (HAS_N && ((fa_ >> u) & 1u)) nf |= 0x00800000u; }
+          if (cb >= 0 && cb < vb.W) { hi = ((wb >> (2 * u)) & 3u) * 0x11u + 0xC4u; if (HAS_N && ((fb_ >> u) & 1u)) nf |= 0x80000000u; }
+          const uint32_t selv = lo | (hi << 8);
+          uint32_t isn = 0u;
+          if (HAS_N) isn = prmt(nf, 0u, 0xBBAAu);
+          uint32_t hd = hoe_up_prev;
+          hoe_up_prev = top.x;
+          uint32_t F = top.y;
+          uint32_t hv[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          uint32_t sp = prmt(profA[k], profB[k], selv);
-          if (HAS_N) sp = (sp & ~isn) | (POS_OE & isn);
-          const uint32_t t = __vadd2(hd, sp);
-          hd = Hoe[k];
-          E[k] = __viaddmax_s16x2(E[k], NEG_EXT, Hoe[k]);
-          const uint32_t fx = __vadd2(F, NEG_EXT);
-          const uint32_t h = __vimax3_s16x2_relu(t, E[k], F);
-          Hoe[k] = __vadd2(h, NEG_OE);
-          F = __viaddmax_s16x2(h, NEG_OE, fx);
-          hv[k] = h;
-        }
-        brow[p * 32] = make_uint2(Hoe[K - 1], F);
-        top = top_next;
-        uint4* dst = hstrip + (size_t)p * CHUNKS * 32;
-        if (BYTES == 1) {
-          // rows 2j, 2j+1 share a word: bytes (A 2j, A 2j+1, B 2j, B 2j+1); one multiply-add per word on the FMA pipe
-          uint32_t wv[K / 2];
+          for (int k = 0; k < K; ++k) {
+            uint32_t sp = prmt(profA[k], profB[k], selv);
+            if (HAS_N) sp = (sp & ~isn) | (POS_OE & isn);
+            const uint32_t t = __vadd2(hd, sp);
+            hd = Hoe[k];
+            E[k] = __viaddmax_s16x2(E[k], NEG_EXT, Hoe[k]);
+            const uint32_t fx = __vadd2(F, NEG_EXT);
+            const uint32_t h = __vimax3_s16x2_relu(t, E[k], F);
+            Hoe[k] = __vadd2(h, NEG_OE);
+            F = __viaddmax_s16x2(h, NEG_OE, fx);
+            hv[k] = h;
+          }
+          brow[p * 32] = make_uint2(Hoe[K - 1], F);
+          if (p == K - 1) corner = Hoe[K - 1];
+          uint4* dst = hstrip + (size_t)p * CHUNKS * 32;
+          if (BYTES == 1) {
+            // rows 2j, 2j+1 share a word: bytes (A 2j, A 2j+1, B 2j, B 2j+1); one multiply-add per word on the FMA pipe
+            uint32_t wv[K / 2];
 #pragma unroll
-          for (int j = 0; j < K / 2; ++j) wv[j] = hv[2 * j + 1] * 256u + hv[2 * j];
+            for (int j = 0; j < K / 2; ++j) wv[j] = hv[2 * j + 1] * 256u + hv[2 * j];
 #pragma unroll
-          for (int c = 0; c < CHUNKS; ++c) dst[c * 32] = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
-        } else {
+            for (int c = 0; c < CHUNKS; ++c) dst[c * 32] = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
+          } else {
 #pragma unroll
-          for (int c = 0; c < CHUNKS; ++c) dst[c * 32] = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+            for (int c = 0; c < CHUNKS; ++c) dst[c * 32] = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+          }
         }
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       p_prev = psteps;
     }
 
@@ -208,8 +243,10 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
           return (uint32_t)reinterpret_cast<const uint16_t*>(hbytes + chunk * 16)[(k & 3) * 2 + half];
         }
       };
-      walk_h_and_emit<HAS_N, false, 16>(a, tA, va, ga, bw, opbuf, [&](int n, int b) -> uint32_t { return cell(n, b, 0); });
-      if (haveB) walk_h_and_emit<HAS_N, false, 16>(a, tB, vb, gb, bw, opbuf, [&](int n, int b) -> uint32_t { return cell(n, b, 1); });
+#pragma unroll 1
+      for (int half = 0; half < (haveB ? 2 : 1); ++half)         // one copy of the walk's code for both tasks
+        walk_h_and_emit<HAS_N, false, 16>(a, half ? tB : tA, half ? vb : va, half ? gb : ga, bw, opbuf,
+                                          [&](int n, int b) -> uint32_t { return cell(n, b, half); });
     }
     __syncwarp();
   }

@@ -134,12 +134,18 @@ inline char* put_u(char* p, uint64_t v) {
 }
 inline char* put_s(char* p, const char* s) { while (*s) *p++ = *s++; return p; }
 
-size_t sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* pool, uint32_t lo, uint32_t hi, const ubu_sw_sam_names* nm,
-                 std::vector<char>& out) {
+}  // namespace
+
+size_t ubu_sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* pool, uint32_t lo, uint32_t hi, const ubu_sw_sam_names* nm,
+                     std::vector<char>& out) {
   static const char bases[4] = {'A', 'C', 'T', 'G'};      // Sequence.java:10-13
   static const char opc[] = "MIDNSHP=X";
   size_t need = 0;
-  for (uint32_t k = lo; k < hi; ++k) need += 160 + (size_t)reads->len[k] + 12 * (size_t)res[k].cigar_n + (nm->qname_prefix ? strlen(nm->qname_prefix) : 0) + 64;
+  const size_t prefix = nm->qname_prefix ? strlen(nm->qname_prefix) : 1;
+  for (uint32_t k = lo; k < hi; ++k) {                    // worst case per line: fixed fields and five 20-digit numbers, the names, SEQ, 11 characters per op
+    const uint32_t w = nm->pair_ref_idx ? nm->pair_ref_idx[k] : k;
+    need += 192 + prefix + (nm->rnames ? strlen(nm->rnames[w]) : 11) + (size_t)reads->len[k] + 11 * (size_t)res[k].cigar_n;
+  }
   out.resize(need);
   char* p = out.data();
   for (uint32_t k = lo; k < hi; ++k) {
@@ -169,8 +175,6 @@ size_t sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint3
   return (size_t)(p - out.data());
 }
 
-}  // namespace
-
 #include <unistd.h>
 
 extern "C" int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* cigar_pool, uint32_t n,
@@ -191,7 +195,7 @@ extern "C" int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_r
     std::vector<std::thread> pool;
     try {
       for (unsigned t = 0; t < m; ++t)
-        pool.emplace_back([&, t] { const uint32_t lo = (b0 + t) * block, hi = std::min<uint32_t>(n, lo + block); used[t] = sam_block(reads, res, cigar_pool, lo, hi, names, bufs[t]); });
+        pool.emplace_back([&, t] { const uint32_t lo = (b0 + t) * block, hi = std::min<uint32_t>(n, lo + block); used[t] = ubu_sam_block(reads, res, cigar_pool, lo, hi, names, bufs[t]); });
     } catch (...) { for (auto& th : pool) th.join(); return UBU_SW_ERR_NOMEM; }
     for (auto& th : pool) th.join();
     for (unsigned t = 0; t < m; ++t) {

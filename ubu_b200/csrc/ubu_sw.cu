@@ -65,7 +65,7 @@ struct PinBuf {
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
     size_t want = n + n / 8 + 256;
-    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocPortable);
     if (e == cudaSuccess) cap = want;
     return e;
   }
@@ -113,6 +113,7 @@ struct Slot {
   bool identity_order = false;           // uniform batch: tasks run in input order, no order array at all
   int lmax = 0, bw_cap = 0;
   unsigned int cig_cap = 0;
+  unsigned int cig_base = 0;             // offset of this batch's ops in the caller's pool (multi-GPU driver), 0 otherwise
   int n_launches = 0;
   // submit()/wait() bookkeeping
   ubu_sw_result* out = nullptr; uint32_t* pool = nullptr; size_t pool_cap = 0;
@@ -494,7 +495,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   int rc = validate_seqs(reads); if (rc) return rc;
   rc = validate_seqs(wins); if (rc) return rc;
   if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
-  s.staged = false; s.ran = false; s.pre_queued = false;
+  s.staged = false; s.ran = false; s.pre_queued = false; s.cig_base = 0;
   s.n_tasks = reads->count;
   s.have_idx = idx != nullptr;
   s.reads_n = reads->nmask != nullptr; s.wins_n = wins->nmask != nullptr;
@@ -613,10 +614,13 @@ int do_run(ubu_sw_handle* h, Slot& s) {
 
   TbArgs a;
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
-  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + CTR_CIG; a.err_flag = s.d_ctr.p + CTR_ERR;
+  a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + CTR_CIG; a.err_flag = s.d_ctr.p + CTR_ERR; a.cig_base = s.cig_base;
   const int max_rows = std::max(s.lmax, 1);
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
+  static const bool tb_serial = env_off("UBU_TB_SERIAL");     // development switch: every traceback kernel on the main stream
+  cudaStream_t ax[kAux];
+  for (int k = 0; k < kAux; ++k) ax[k] = tb_serial ? st : s.aux[k];
   CU(h, cudaEventRecord(s.ev_fork, st));
   for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
   if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
@@ -635,9 +639,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
         CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
       }
-      k8<<<grid, TB_THREADS, sm8, s.aux[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, s.aux[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, s.aux[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
+      k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
     } else {
       auto k8 = tb_fill_reg_kernel<8, false, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, false, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, false, TB_THREADS>;
       if (sm32 > 48 * 1024) {
@@ -645,9 +649,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
         CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
       }
-      k8<<<grid, TB_THREADS, sm8, s.aux[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, s.aux[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, s.aux[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
+      k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
+      k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
+      k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
     }
     s.n_launches += 3;
   }
@@ -657,10 +661,10 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     sa.lists = s.d_lists.p; sa.counts = s.d_ctr.p; sa.work = s.d_ctr.p + CTR_WORK; sa.n_slots = s.n_slots;
     sa.hstore = s.d_strip.p; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + s.strip_bnd_off);
     sa.rows_cap = s.caps.rows_cap; sa.bw_cap = s.caps.bw_cap;
-    CU(h, launch_strip(s.any_n, def, s.strip_bytes, s.strip_grid, a, sa, s.aux[2]));
+    CU(h, launch_strip(s.any_n, def, s.strip_bytes, s.strip_grid, a, sa, ax[2]));
     ++s.n_launches;
   }
-  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, s.aux[3]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
+  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[3]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
                                                           s.d_wide.p, max_rows, s.bw_cap);
   CU(h, cudaGetLastError()); ++s.n_launches;
   for (int k = 0; k < kAux; ++k) {                    // join
@@ -1018,6 +1022,262 @@ int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_
   return ubu_sw_wait(h, ticket, cigar_pool_used);
 }
 
+// ================================= multi-GPU driver ==============================================
+// One process, N GPUs: a host thread and a handle per device; the batch is cut into input-order chunks,
+// chunk c belongs to device c mod N and travels through that handle's slots. There is no merge pass on the host: every chunk
+// owns a slice of the caller's CIGAR pool proportional to its reads, the kernels write final cigar_off values (TbArgs::cig_base)
+// and both the records and the ops are copied by the GPU straight into their input-order places in the caller's arrays.
+// "Ordered merge" is then only the order in which finished chunks are released to the SAM writer.
+}  // extern "C"
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <unistd.h>
+
+size_t ubu_sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* pool, uint32_t lo, uint32_t hi,
+                     const ubu_sw_sam_names* nm, std::vector<char>& out);       // ubu_pack.cu
+
+struct ubu_sw_multi {
+  std::vector<ubu_sw_handle*> hs;
+  uint32_t chunk = 1u << 16;
+  std::string last_error;
+};
+
+namespace {
+
+// Views of reads [lo, hi) and of the windows they use. True: the chunk's bytes are ascending stretches (what every packer
+// produces from coordinate-sorted input) and only those stretches go to the device (bias). False: the views name the
+// caller's whole buffers (correct for any layout, but every chunk then uploads all of them).
+bool chunk_views(const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, uint32_t lo, uint32_t hi,
+                 ubu_sw_seqs& rs, ubu_sw_seqs& ws, StageBias& bias, const uint32_t*& ix) {
+  const uint32_t m = hi - lo;
+  auto stretch = [](const uint32_t* off, const uint16_t* len, uint32_t k, uint32_t per, uint64_t limit, size_t& b0, size_t& bytes) -> bool {
+    const uint64_t end = (uint64_t)off[k - 1] + ((uint32_t)len[k - 1] + per - 1u) / per;
+    b0 = off[0]; bytes = (size_t)(end - off[0]);
+    return end <= limit && ascending(off, len, k, per);
+  };
+  rs = *reads; ws = *wins; bias = StageBias{};
+  rs.off = reads->off + lo; rs.len = reads->len + lo; rs.count = m;
+  if (reads->nmask) rs.nmask_off = reads->nmask_off + lo;
+  ix = idx ? idx + lo : nullptr;
+  bool ok = stretch(rs.off, rs.len, m, 4, reads->packed_bytes, bias.rp, bias.r_bytes);
+  if (ok && reads->nmask) ok = stretch(rs.nmask_off, rs.len, m, 8, reads->nmask_bytes, bias.rn, bias.rn_bytes);
+  uint32_t w0 = lo, w1 = hi;
+  if (ok && idx) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0;
+    minmax_u32(idx + lo, m, mn, mx);
+    ok = mx < wins->count && (uint64_t)(mx - mn) + 1u <= 2ull * m + 16ull;
+    w0 = mn; w1 = mx + 1u;
+  }
+  if (ok) {
+    const uint32_t mw = w1 - w0;
+    ws.off = wins->off + w0; ws.len = wins->len + w0; ws.count = mw;
+    bias.w = idx ? w0 : 0u;
+    ok = stretch(ws.off, ws.len, mw, 4, wins->packed_bytes, bias.wp, bias.w_bytes);
+    if (ok && wins->nmask) { ws.nmask_off = wins->nmask_off + w0; ok = stretch(ws.nmask_off, ws.len, mw, 8, wins->nmask_bytes, bias.wn, bias.wn_bytes); }
+  }
+  if (ok) return true;
+  rs.packed = reads->packed; ws = *wins; bias = StageBias{};            // whole buffers
+  if (!idx) { ws.off = wins->off + lo; ws.len = wins->len + lo; ws.count = m; if (wins->nmask) ws.nmask_off = wins->nmask_off + lo; }
+  return false;
+}
+
+struct MultiRun {
+  ubu_sw_multi* m;
+  const ubu_sw_seqs *reads, *wins; const uint32_t* idx;
+  ubu_sw_result* out; uint32_t* pool; size_t pool_cap;
+  uint32_t n, chunk, n_chunks;
+  std::vector<std::atomic<int>> done;          // per chunk: 1 = records and ops are in the caller's arrays
+  std::vector<uint32_t> need;                  // per chunk: CIGAR ops it produced
+  std::atomic<int> failed{0};                  // first failing status
+  std::mutex mu; std::condition_variable cv;
+  MultiRun(uint32_t nc) : done(nc), need(nc, 0u) { for (auto& d : done) d.store(0); }
+  uint64_t base_of(uint32_t c) const { return (uint64_t)pool_cap * std::min<uint64_t>((uint64_t)c * chunk, n) / n; }
+  void fail(int rc) { int z = 0; failed.compare_exchange_strong(z, rc); cv.notify_all(); }
+};
+
+// the worker of one device: its chunks, in order, through the handle's slots
+void multi_worker(MultiRun* R, int d) {
+  ubu_sw_handle* h = R->m->hs[d];
+  const int nd = (int)R->m->hs.size();
+  if (cudaSetDevice(h->device) != cudaSuccess) { R->fail(UBU_SW_ERR_CUDA); return; }
+  int head = 0, inflight = 0;
+  uint32_t chunk_of_slot[kMaxSlots];
+  auto finish = [&](int slot) -> int {
+    Slot& s = h->slots[slot];
+    const uint32_t c = chunk_of_slot[slot];
+    const uint64_t base = R->base_of(c), cap = R->base_of(c + 1) - base;
+    size_t used = 0;
+    int rc = do_fetch(h, s, R->out + s.st_lo, R->pool ? R->pool + base : nullptr, (size_t)cap, &used);
+    R->need[c] = (uint32_t)used;
+    if (rc && rc != UBU_SW_ERR_CIGAR_POOL) return rc;
+    if (rc == UBU_SW_ERR_CIGAR_POOL) R->fail(rc);                       // the slice was too small: the call reports the capacity it needs
+    R->done[c].store(1, std::memory_order_release);
+    { std::lock_guard<std::mutex> lk(R->mu); }
+    R->cv.notify_all();
+    return UBU_SW_OK;
+  };
+  int rc = UBU_SW_OK;
+  for (uint32_t c = (uint32_t)d; c < R->n_chunks && !rc; c += (uint32_t)nd) {
+    if (R->failed.load() && R->failed.load() != UBU_SW_ERR_CIGAR_POOL) break;
+    if (inflight == h->n_slots) { rc = finish(head); head = (head + 1) % h->n_slots; --inflight; if (rc) break; }
+    const int slot = (head + inflight) % h->n_slots;
+    Slot& s = h->slots[slot];
+    const uint32_t lo = c * R->chunk, hi = (uint32_t)std::min<uint64_t>(R->n, (uint64_t)lo + R->chunk);
+    ubu_sw_seqs rs, ws; StageBias bias; const uint32_t* ix;
+    const bool compact = chunk_views(R->reads, R->wins, R->idx, lo, hi, rs, ws, bias, ix);
+    rc = do_stage(h, s, &rs, &ws, ix, compact, compact ? &bias : nullptr); if (rc) break;
+    const uint64_t base = R->base_of(c), cap = R->base_of(c + 1) - base;
+    s.cig_base = (unsigned int)base;
+    rc = do_run(h, s); if (rc) break;
+    rc = enqueue_early_d2h(h, s, R->out + lo, R->pool ? R->pool + base : nullptr, (size_t)cap); if (rc) break;
+    s.st_lo = lo; s.st_hi = hi; chunk_of_slot[slot] = c;
+    ++inflight;
+  }
+  while (inflight) { const int r2 = finish(head); if (r2 && !rc) rc = r2; head = (head + 1) % h->n_slots; --inflight; }
+  if (rc) {
+    for (int k = 0; k < h->n_slots; ++k) if (h->slots[k].stream) cudaStreamSynchronize(h->slots[k].stream);
+    R->m->last_error = h->last_error;
+    R->fail(rc);
+  }
+}
+
+int multi_align(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* wins, const uint32_t* idx, ubu_sw_result* out,
+                uint32_t* pool, size_t pool_cap, size_t* used_out, int fd, const ubu_sw_sam_names* names, int sam_threads,
+                uint64_t* bytes_out, bool want_sam) {
+  if (used_out) *used_out = 0;
+  if (bytes_out) *bytes_out = 0;
+  if (!m || m->hs.empty() || !reads || !wins) return UBU_SW_ERR_ARG;
+  int rc = validate_seqs(reads); if (rc) return rc;
+  rc = validate_seqs(wins); if (rc) return rc;
+  if (!idx && reads->count != wins->count) return UBU_SW_ERR_ARG;
+  const uint32_t n = reads->count;
+  if (n == 0) return UBU_SW_OK;
+  if (!out || (want_sam && !names)) return UBU_SW_ERR_ARG;
+  for (ubu_sw_handle* h : m->hs) for (int k = 0; k < h->n_slots; ++k) if (h->slots[k].pending) return UBU_SW_ERR_BUSY;
+  pool_cap = std::min<size_t>(pool_cap, 0xFFFFFFFFull);                      // cigar_off is 32 bits
+  const uint32_t n_chunks = (uint32_t)(((uint64_t)n + m->chunk - 1) / m->chunk);
+  MultiRun R(n_chunks);
+  R.m = m; R.reads = reads; R.wins = wins; R.idx = idx; R.out = out; R.pool = pool; R.pool_cap = pool ? pool_cap : 0;
+  R.n = n; R.chunk = m->chunk; R.n_chunks = n_chunks;
+  std::vector<std::thread> workers;
+  try {
+    for (size_t d = 0; d < m->hs.size(); ++d) workers.emplace_back(multi_worker, &R, (int)d);
+  } catch (...) { R.fail(UBU_SW_ERR_NOMEM); }
+
+  // ---- ordered release of finished chunks: SAM text formatted on helper threads, written in input order ----
+  uint64_t total_bytes = 0;
+  if (want_sam) {
+    unsigned nt = sam_threads > 0 ? (unsigned)sam_threads : std::max(2u, std::thread::hardware_concurrency());
+    nt = std::max(1u, std::min<unsigned>(nt, n_chunks));
+    const unsigned ring = nt + 2;
+    std::vector<std::vector<char>> bufs(ring);
+    std::vector<size_t> blen(ring, 0);
+    std::vector<std::atomic<int>> formatted(n_chunks);
+    for (auto& f : formatted) f.store(0);
+    std::atomic<uint32_t> next_fmt{0}, written{0};
+    std::vector<std::thread> fmt;
+    auto formatter = [&] {
+      for (;;) {
+        const uint32_t c = next_fmt.fetch_add(1);
+        if (c >= n_chunks) return;
+        {   // wait for the chunk's results and for its ring buffer to be free
+          std::unique_lock<std::mutex> lk(R.mu);
+          R.cv.wait(lk, [&] { return (R.failed.load() != 0) || (R.done[c].load(std::memory_order_acquire) && c < written.load() + ring); });
+          if (R.failed.load()) return;
+        }
+        const uint32_t lo = c * R.chunk, hi = (uint32_t)std::min<uint64_t>(n, (uint64_t)lo + R.chunk);
+        blen[c % ring] = ubu_sam_block(reads, out, pool, lo, hi, names, bufs[c % ring]);
+        formatted[c].store(1, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(R.mu); }
+        R.cv.notify_all();
+      }
+    };
+    try { for (unsigned t = 0; t < nt; ++t) fmt.emplace_back(formatter); } catch (...) { R.fail(UBU_SW_ERR_NOMEM); }
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      {
+        std::unique_lock<std::mutex> lk(R.mu);
+        R.cv.wait(lk, [&] { return R.failed.load() != 0 || formatted[c].load(std::memory_order_acquire) != 0; });
+        if (R.failed.load()) break;
+      }
+      const std::vector<char>& b = bufs[c % ring];
+      size_t off = 0;
+      while (fd >= 0 && off < blen[c % ring]) {
+        const ssize_t wr = write(fd, b.data() + off, blen[c % ring] - off);
+        if (wr <= 0) { R.fail(UBU_SW_ERR_ARG); break; }
+        off += (size_t)wr;
+      }
+      total_bytes += blen[c % ring];
+      written.store(c + 1);
+      { std::lock_guard<std::mutex> lk(R.mu); }
+      R.cv.notify_all();
+    }
+    for (auto& t : fmt) t.join();
+  }
+  for (auto& t : workers) t.join();
+  uint64_t high = 0; double per_read = 0.0;
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t lo = c * R.chunk, hi = (uint32_t)std::min<uint64_t>(n, (uint64_t)lo + R.chunk);
+    high = std::max<uint64_t>(high, R.base_of(c) + R.need[c]);
+    per_read = std::max(per_read, (double)R.need[c] / (double)(hi - lo));
+  }
+  const int failed = R.failed.load();
+  if (failed == UBU_SW_ERR_CIGAR_POOL) {                                     // capacity with which every slice would have been large enough
+    if (used_out) *used_out = (size_t)(per_read * (double)n) + n_chunks + 64;
+    return failed;
+  }
+  if (failed) return failed;
+  if (used_out) *used_out = (size_t)high;
+  if (bytes_out) *bytes_out = total_bytes;
+  return UBU_SW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ubu_sw_multi_create(const ubu_sw_params* params, const int* devices, int n_devices, int slots, uint32_t chunk_reads, ubu_sw_multi** out) {
+  if (!out) return UBU_SW_ERR_ARG;
+  *out = nullptr;
+  const int visible = ubu_sw_device_count();
+  if (visible <= 0) return UBU_SW_ERR_NO_DEVICE;
+  if (!devices) n_devices = n_devices > 0 ? std::min(n_devices, visible) : visible;
+  if (n_devices <= 0) return UBU_SW_ERR_ARG;
+  ubu_sw_multi* m = new (std::nothrow) ubu_sw_multi();
+  if (!m) return UBU_SW_ERR_NOMEM;
+  if (chunk_reads) m->chunk = std::max<uint32_t>(chunk_reads, 256u);
+  for (int k = 0; k < n_devices; ++k) {
+    ubu_sw_handle* h = nullptr;
+    const int rc = ubu_sw_create(params, devices ? devices[k] : k, slots, &h);
+    if (rc) { ubu_sw_multi_destroy(m); return rc; }
+    m->hs.push_back(h);
+  }
+  *out = m;
+  return UBU_SW_OK;
+}
+
+void ubu_sw_multi_destroy(ubu_sw_multi* m) {
+  if (!m) return;
+  for (ubu_sw_handle* h : m->hs) ubu_sw_destroy(h);
+  delete m;
+}
+
+int ubu_sw_multi_device_count(const ubu_sw_multi* m) { return m ? (int)m->hs.size() : 0; }
+const char* ubu_sw_multi_last_error(ubu_sw_multi* m) { return m ? m->last_error.c_str() : ""; }
+
+int ubu_sw_multi_align(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                       ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used) {
+  return multi_align(m, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, cigar_pool_used, -1, nullptr, 0, nullptr, false);
+}
+
+int ubu_sw_multi_align_sam(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, const uint32_t* pair_ref_idx,
+                           ubu_sw_result* out, uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used,
+                           int fd, const ubu_sw_sam_names* names, int sam_threads, uint64_t* bytes_written) {
+  return multi_align(m, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, cigar_pool_used, fd, names, sam_threads, bytes_written, true);
+}
+
 int ubu_sw_load_refs(ubu_sw_handle* h, const ubu_sw_refs* r) {
   if (!h || !r || (r->count && (!r->packed || !r->off || !r->len)) || (r->nmask && !r->nmask_off)) return UBU_SW_ERR_ARG;
   for (uint32_t k = 0; k < r->count; ++k) {
@@ -1153,7 +1413,7 @@ int ubu_sw_debug_plan(const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, cons
 
 void* ubu_sw_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return p;
 }
 void ubu_sw_host_free(void* p) { if (p) cudaFreeHost(p); }
