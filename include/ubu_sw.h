@@ -121,6 +121,10 @@ int ubu_sw_fetch(ubu_sw_handle* h, int slot, ubu_sw_result* out,
 int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]);
 /* Number of kernel launches issued by the last run() on the slot. */
 int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot);
+/* Diagnostics: device counters of the last run() on the slot (valid after run): out[0..9] = tasks per traceback class (0 gap-free scan,
+ * 1-3 register bands of 8/16/32 diagonals, 4-8 strip classes by band width, 9 scalar last resort), out[10] = CIGAR ops produced,
+ * out[11] = error flags, out[12] = strip work units drawn. */
+int ubu_sw_debug_counters(ubu_sw_handle* h, int slot, uint32_t out[16]);
 
 /* ---- one process, several GPUs (BASELINE.json configs[4]) -------------------------------------------
  * The reference hands parallelism to `bwa -t numThreads` (Aligner.java:19,49) and treats its inputs as independent work

@@ -67,7 +67,7 @@ def main():
             nchk, bad = check(al, w, res, a.check, threads)
             row = {"config": name, "tasks": w.n_tasks, "cells": w.cells, "ms": float(m[0]), "fwd_ms": float(m[1]), "tb_ms": float(m[2]),
                    "gcups": w.cells / (m[0] * 1e-3) / 1e9, "reads_per_s": w.n_tasks / (m[0] * 1e-3), "launches": al.last_run_launches(0),
-                   "unaligned": int((res.results["flags"] & 1).sum()), "checked": nchk, "mismatching": bad, "gen_s": round(tgen, 1)}
+                   "unaligned": int((res.results["flags"] & 1).sum()), "tb_classes": [int(x) for x in al.debug_counters(0)[:10]], "checked": nchk, "mismatching": bad, "gen_s": round(tgen, 1)}
             out.append(row)
             print(json.dumps(row), flush=True)
     return 1 if any(r["mismatching"] for r in out) else 0

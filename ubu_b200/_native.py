@@ -69,6 +69,7 @@ SYMBOLS = [
     ("ubu_sw_fetch", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("ubu_sw_last_run_ms", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     ("ubu_sw_last_run_launches", C.c_int, [C.c_void_p, C.c_int]),
+    ("ubu_sw_debug_counters", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("ubu_sw_multi_create", C.c_int, [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]),
     ("ubu_sw_multi_destroy", None, [C.c_void_p]),
     ("ubu_sw_multi_device_count", C.c_int, [C.c_void_p]),

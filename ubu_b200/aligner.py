@@ -149,6 +149,12 @@ class SwAligner:
     def last_run_launches(self, slot: int) -> int:
         return int(self._lib.ubu_sw_last_run_launches(self._h, slot))
 
+    def debug_counters(self, slot: int) -> np.ndarray:
+        """Tasks per traceback class [0..9], CIGAR ops [10], error flags [11], strip work units [12] of the last run()."""
+        out = np.zeros(16, dtype=np.uint32)
+        self._check(self._lib.ubu_sw_debug_counters(self._h, slot, out.ctypes.data))
+        return out
+
     # -- pipelined calls (ubu_sw_submit / ubu_sw_wait) -------------------------------------------
     def submit(self, reads: SeqSet, windows: SeqSet, pair_ref_idx: Optional[np.ndarray], res: np.ndarray,
                pool: np.ndarray) -> int:

@@ -31,6 +31,7 @@ namespace ubu {
 
 constexpr int TBS_K = 16;                 // rows per strip
 constexpr int TBS_THREADS = 128;
+constexpr int TBS_BW_MAX = 288;          // widest band taken (the walk keeps <= bw + 8 CIGAR runs in local memory)
 #ifndef UBU_TBS_MIN_BLOCKS
 #define UBU_TBS_MIN_BLOCKS 3
 #endif
@@ -72,7 +73,7 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
   unsigned char* hwarp = sa.hstore + (size_t)warp_global * tbs_hstore_bytes_per_warp(sa.rows_cap, sa.bw_cap, BYTES);
   uint2* bnd = sa.boundary + (size_t)warp_global * (tbs_boundary_bytes_per_warp(sa.rows_cap, sa.bw_cap) / 8u) + lane;
   uint4* hlane = reinterpret_cast<uint4*>(hwarp) + lane;         // chunk (step, c) of this lane at hlane[(step * CHUNKS + c) * 32]
-  uint32_t opbuf[2 * 96 + 16];                                   // CIGAR runs of one walk (local memory; <= 2 * gaps + 3 runs)
+  uint32_t opbuf[TBS_BW_MAX + 16];                               // CIGAR runs of one walk (local memory; <= 2 * gaps + 3 <= bw + 2 runs)
   // boundary staging: per warp a double buffer of 16 steps x 32 lanes x 8 bytes
   __shared__ __align__(16) uint2 sm_all[(TBS_THREADS / 32) * 2 * 16 * 32];
   const uint2* sm_mine = sm_all + (threadIdx.x >> 5) * (2 * 16 * 32) + lane;
@@ -111,7 +112,7 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
       bw = max((fa.i_hi - fa.i_lo) + 2 * gap_bound(sc, fa.i_hi, fa.score) + 1, (fb.i_hi - fb.i_lo) + 2 * gap_bound(sc, fb.i_hi, fb.score) + 1);
       ga = make_band(sc, fa, bw); gb = make_band(sc, fb, bw);
       nrows = max(ga.rows, gb.rows);
-      if (bw > sa.bw_cap || nrows > sa.rows_cap || bw > 2 * 96 + 8) { atomicOr(a.err_flag, 2u); ok = false; }
+      if (bw > sa.bw_cap || nrows > sa.rows_cap || bw > TBS_BW_MAX) { atomicOr(a.err_flag, 2u); ok = false; }
     }
     if (!ok) { bw = 0; nrows = 0; }
     int pw = ok ? K + bw - 1 : 0;                                // steps per strip, warp-wide maximum = row pitch of the store

@@ -36,7 +36,7 @@ constexpr size_t kMaxDynSmem = 200 * 1024;
 
 constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceback: one thread per task pair
 constexpr int TBS_GRID_PER_SM = UBU_TBS_MIN_BLOCKS;      // wide bands: row strips in registers, one thread per task pair (sw_tbstrip.cuh)
-constexpr int kStripBwCap = 200;                         // widest band the strip kernel takes (its walk keeps <= bw + 8 CIGAR runs)
+constexpr int kStripBwCap = TBS_BW_MAX;                  // widest band the strip kernel takes: every band default scoring allows for reads <= 256 bp
 constexpr size_t kStripScratchBudget = (size_t)6 << 30;  // per pipeline slot; fewer CTAs are launched when a batch's worst case would need more
 constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, strip work counter
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
@@ -847,6 +847,18 @@ int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]) {
   CU(h, cudaEventElapsedTime(&ms[0], s.ev[0], s.ev[2]));
   CU(h, cudaEventElapsedTime(&ms[1], s.ev[0], s.ev[1]));
   CU(h, cudaEventElapsedTime(&ms[2], s.ev[1], s.ev[2]));
+  return UBU_SW_OK;
+}
+
+// Diagnostics: the device counters of the last run() on the slot, copied out after a sync: [0..TB_CLASSES) tasks per traceback
+// class (0 gap-free, 1-3 register bands, 4-8 strip classes, 9 scalar), then CIGAR ops produced, error flags, strip work units.
+int ubu_sw_debug_counters(ubu_sw_handle* h, int slot, uint32_t out[16]) {
+  if (!h || slot < 0 || slot >= h->n_slots || !out) return UBU_SW_ERR_ARG;
+  Slot& s = h->slots[slot];
+  if (!s.ran || !s.d_ctr.p) return UBU_SW_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(s.stream));
+  CU(h, cudaMemcpy(out, s.d_ctr.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return UBU_SW_OK;
 }
 
