@@ -21,8 +21,10 @@
 // WALK. walk_h_and_emit (sw_tb.cuh) on the stored H, diagonal test from the sequences, 17 cells of the current diagonal per
 // round trip; each lane walks its task A, then its task B.
 //
-// SCHEDULING. One launch serves all strip classes (tasks filed by band width in the forward epilogue, widest first, so that a
-// warp's 32 pairs have similar trip counts); warps draw units of 32 pairs from a device counter.
+// SCHEDULING. Tasks are filed by band width in the forward epilogue; a launch serves a range of those classes, widest first, so
+// that a warp's 32 pairs have similar trip counts; warps draw units of 32 pairs from a device counter. The host issues two
+// launches side by side: one for bands up to 120 diagonals (scratch sized for that width, full grid) and a small one for the
+// rare wider bands (scratch sized for the widest band the batch's scoring allows).
 #pragma once
 #include "sw_common.cuh"
 #include "sw_tb.cuh"
@@ -32,6 +34,9 @@ namespace ubu {
 constexpr int TBS_K = 16;                 // rows per strip
 constexpr int TBS_THREADS = 128;
 constexpr int TBS_BW_MAX = 288;          // widest band taken (the walk keeps <= bw + 8 CIGAR runs in local memory)
+#ifndef UBU_TBS_WB
+#define UBU_TBS_WB 16                    // cells of the current diagonal fetched per round trip of the walk
+#endif
 #ifndef UBU_TBS_MIN_BLOCKS
 #define UBU_TBS_MIN_BLOCKS 3
 #endif
@@ -48,7 +53,8 @@ __host__ __device__ inline size_t tbs_boundary_bytes_per_warp(int rows_cap, int 
 struct StripArgs {
   const uint32_t* lists;          // [TB_CLASSES][n_slots]
   const unsigned int* counts;     // [TB_CLASSES]
-  unsigned int* work;             // unit counter (zeroed before the launch)
+  unsigned int* work;             // unit counter of this launch (zeroed before it)
+  int cls_lo, cls_hi;             // traceback classes served (a launch for the common widths, one for the rare very wide bands)
   uint32_t n_slots;
   unsigned char* hstore;          // [warps of the grid] x tbs_hstore_bytes_per_warp
   uint2* boundary;                // [warps of the grid] x tbs_boundary_bytes_per_warp
@@ -79,26 +85,23 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
   const uint2* sm_mine = sm_all + (threadIdx.x >> 5) * (2 * 16 * 32) + lane;
   const uint32_t sm_bnd = (uint32_t)__cvta_generic_to_shared(sm_mine);
 
-  // units of 32 pairs, widest class first
-  unsigned int cnt[TB_STRIP_CLASSES], unit_end[TB_STRIP_CLASSES];
+  // units of 32 pairs over the classes this launch serves, widest class first
   unsigned int total_units = 0;
-#pragma unroll
-  for (int c = 0; c < TB_STRIP_CLASSES; ++c) {
-    cnt[c] = sa.counts[TB_STRIP_FIRST + TB_STRIP_CLASSES - 1 - c];
-    total_units += ((cnt[c] + 1u) / 2u + 31u) / 32u;
-    unit_end[c] = total_units;
-  }
+  for (int c = sa.cls_hi; c >= sa.cls_lo; --c) total_units += ((sa.counts[c] + 1u) / 2u + 31u) / 32u;
 
   for (;;) {
     unsigned int unit = 0;
     if (lane == 0) unit = atomicAdd(sa.work, 1u);
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= total_units) break;
-    int cls = 0; unsigned int ubase = 0;
-#pragma unroll
-    for (int c = 0; c < TB_STRIP_CLASSES - 1; ++c) if (unit >= unit_end[c]) { cls = c + 1; ubase = unit_end[c]; }
-    const uint32_t* list = sa.lists + (size_t)(TB_STRIP_FIRST + TB_STRIP_CLASSES - 1 - cls) * sa.n_slots;
-    const unsigned int n_tasks = cnt[cls], n_pairs = (n_tasks + 1u) / 2u;
+    int cls = sa.cls_hi; unsigned int ubase = 0, n_tasks = sa.counts[cls];
+    for (;;) {                                                   // the class this unit falls into
+      const unsigned int nu = ((n_tasks + 1u) / 2u + 31u) / 32u;
+      if (unit < ubase + nu || cls == sa.cls_lo) break;
+      ubase += nu; --cls; n_tasks = sa.counts[cls];
+    }
+    const uint32_t* list = sa.lists + (size_t)cls * sa.n_slots;
+    const unsigned int n_pairs = (n_tasks + 1u) / 2u;
     const unsigned int pair = (unit - ubase) * 32u + (unsigned)lane;
     const bool have = pair < n_pairs, haveB = have && 2u * pair + 1u < n_tasks;
     const uint32_t tA = have ? list[2u * pair] : 0u, tB = haveB ? list[2u * pair + 1u] : tA;
@@ -246,7 +249,7 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
       };
 #pragma unroll 1
       for (int half = 0; half < (haveB ? 2 : 1); ++half)         // one copy of the walk's code for both tasks
-        walk_h_and_emit<HAS_N, false, 16>(a, half ? tB : tA, half ? vb : va, half ? gb : ga, bw, opbuf,
+        walk_h_and_emit<HAS_N, false, UBU_TBS_WB>(a, half ? tB : tA, half ? vb : va, half ? gb : ga, bw, opbuf,
                                           [&](int n, int b) -> uint32_t { return cell(n, b, half); });
     }
     __syncwarp();

@@ -38,7 +38,8 @@ constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceb
 constexpr int TBS_GRID_PER_SM = UBU_TBS_MIN_BLOCKS;      // wide bands: row strips in registers, one thread per task pair (sw_tbstrip.cuh)
 constexpr int kStripBwCap = TBS_BW_MAX;                  // widest band the strip kernel takes: every band default scoring allows for reads <= 256 bp
 constexpr size_t kStripScratchBudget = (size_t)6 << 30;  // per pipeline slot; fewer CTAs are launched when a batch's worst case would need more
-constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, strip work counter
+constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, two strip work counters
+constexpr int kStripBwCommon = 120;                      // bands up to this width go to the full-grid strip launch (TB classes 4..7)
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
 constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
 
@@ -92,7 +93,8 @@ struct Slot {
   int tb_grid = 1;                       // CTAs of the register-band kernels (sized by the batch)
   StripCaps caps{0, 0};
   DevBuf<unsigned char> d_strip;         // H store + boundary arrays of the strip kernel's warps
-  size_t strip_bnd_off = 0; int strip_grid = 0, strip_bytes = 1;
+  struct StripLaunch { int grid = 0, bw_cap = 0, cls_lo = 0, cls_hi = 0; size_t h_off = 0, b_off = 0; } strip[2];   // common widths | very wide
+  int strip_bytes = 1;
   int tbw_grid = 1;
   bool pre_queued = false; size_t pre_words = 0;   // early device->host copies queued by submit()
   DevBuf<unsigned char> d_wide;          // scratch of the scalar last-resort traceback kernel
@@ -543,19 +545,29 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     s.h_off[2] = s.h_off[1] + reg_threads * (size_t)max_rows * 16;
     const size_t hwords = s.h_off[2] + reg_threads * (size_t)max_rows * 32;
     // wide bands: strip kernel. One byte per stored H when no score of the batch can exceed 255, else two.
-    s.caps.rows_cap = 0; s.caps.bw_cap = 0; s.strip_grid = 0;
+    s.caps.rows_cap = 0; s.caps.bw_cap = 0; s.strip[0].grid = s.strip[1].grid = 0;
     if (s.bw_cap > 32) {
       s.caps.rows_cap = max_rows; s.caps.bw_cap = std::min(s.bw_cap, kStripBwCap);
       s.strip_bytes = (h->sc.match * max_rows <= 255) ? 1 : 2;
-      const size_t per_warp_h = tbs_hstore_bytes_per_warp(s.caps.rows_cap, s.caps.bw_cap, s.strip_bytes),
-                   per_warp_b = tbs_boundary_bytes_per_warp(s.caps.rows_cap, s.caps.bw_cap);
-      const size_t per_cta = (per_warp_h + per_warp_b) * (TBS_THREADS / 32);
       const size_t strip_ctas = ((size_t)(n + 1) / 2 + TBS_THREADS - 1) / TBS_THREADS;
-      size_t grid = std::min<size_t>((size_t)h->sm_count * TBS_GRID_PER_SM, strip_ctas);
-      grid = std::max<size_t>(1, std::min<size_t>(grid, kStripScratchBudget / per_cta));
-      s.strip_grid = (int)grid;
-      s.strip_bnd_off = grid * (TBS_THREADS / 32) * per_warp_h;
-      CU(h, s.d_strip.reserve(s.strip_bnd_off + grid * (TBS_THREADS / 32) * per_warp_b + 256));
+      size_t bytes = 0;
+      for (int k = 0; k < 2; ++k) {
+        Slot::StripLaunch& L = s.strip[k];
+        L.cls_lo = k == 0 ? TB_STRIP_FIRST : TB_STRIP_FIRST + TB_STRIP_CLASSES - 1;
+        L.cls_hi = k == 0 ? TB_STRIP_FIRST + TB_STRIP_CLASSES - 2 : TB_STRIP_FIRST + TB_STRIP_CLASSES - 1;
+        L.bw_cap = k == 0 ? std::min(s.caps.bw_cap, kStripBwCommon) : s.caps.bw_cap;
+        if (k == 1 && s.caps.bw_cap <= kStripBwCommon) continue;            // no band of this batch can be that wide
+        const size_t per_warp_h = tbs_hstore_bytes_per_warp(s.caps.rows_cap, L.bw_cap, s.strip_bytes),
+                     per_warp_b = tbs_boundary_bytes_per_warp(s.caps.rows_cap, L.bw_cap);
+        const size_t per_cta = (per_warp_h + per_warp_b) * (TBS_THREADS / 32);
+        // the wide launch sees ~2 % of an indel-rich batch: a quarter of the SMs' worth of CTAs is plenty
+        size_t grid = std::min<size_t>(k == 0 ? (size_t)h->sm_count * TBS_GRID_PER_SM : (size_t)(h->sm_count + 1) / 2, strip_ctas);
+        grid = std::max<size_t>(1, std::min<size_t>(grid, kStripScratchBudget / per_cta));
+        L.grid = (int)grid;
+        L.h_off = bytes; bytes += grid * (TBS_THREADS / 32) * per_warp_h;
+        L.b_off = bytes; bytes += grid * (TBS_THREADS / 32) * per_warp_b;
+      }
+      CU(h, s.d_strip.reserve(bytes + 256));
     }
     CU(h, s.d_hstore.reserve(hwords));
     {
@@ -655,16 +667,19 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     }
     s.n_launches += 3;
   }
-  if (s.strip_grid > 0) {                             // wide bands: one launch serves all strip classes, widest first
+  for (int k = 1; k >= 0; --k) {                       // wide bands: the rare very wide ones first, then the common widths
+    const Slot::StripLaunch& L = s.strip[k];
+    if (L.grid <= 0) continue;
     const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
     StripArgs sa;
-    sa.lists = s.d_lists.p; sa.counts = s.d_ctr.p; sa.work = s.d_ctr.p + CTR_WORK; sa.n_slots = s.n_slots;
-    sa.hstore = s.d_strip.p; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + s.strip_bnd_off);
-    sa.rows_cap = s.caps.rows_cap; sa.bw_cap = s.caps.bw_cap;
-    CU(h, launch_strip(s.any_n, def, s.strip_bytes, s.strip_grid, a, sa, ax[2]));
+    sa.lists = s.d_lists.p; sa.counts = s.d_ctr.p; sa.work = s.d_ctr.p + CTR_WORK + k; sa.n_slots = s.n_slots;
+    sa.cls_lo = L.cls_lo; sa.cls_hi = L.cls_hi;
+    sa.hstore = s.d_strip.p + L.h_off; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + L.b_off);
+    sa.rows_cap = s.caps.rows_cap; sa.bw_cap = L.bw_cap;
+    CU(h, launch_strip(s.any_n, def, s.strip_bytes, L.grid, a, sa, k == 0 ? ax[2] : ax[3]));
     ++s.n_launches;
   }
-  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[3]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
+  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[1]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
                                                           s.d_wide.p, max_rows, s.bw_cap);
   CU(h, cudaGetLastError()); ++s.n_launches;
   for (int k = 0; k < kAux; ++k) {                    // join
