@@ -35,15 +35,18 @@ typedef enum {
   UBU_SW_ERR_ARG = -1,          /* NULL pointer, bad parameter range, bad index          */
   UBU_SW_ERR_CUDA = -2,         /* CUDA runtime failure; ubu_sw_last_error() has the text */
   UBU_SW_ERR_CIGAR_POOL = -3,   /* cigar_pool_cap too small; *cigar_pool_used = required  */
-  UBU_SW_ERR_TOO_LONG = -4,     /* read longer than UBU_SW_MAX_READ                       */
+  UBU_SW_ERR_TOO_LONG = -4,     /* read longer than UBU_SW_MAX_READ, or a long read whose matrix exceeds UBU_SW_MAX_LONG_CELLS */
   UBU_SW_ERR_NO_DEVICE = -5,    /* no CUDA device / not an sm_100 device                  */
   UBU_SW_ERR_BUSY = -6,         /* no free pipeline slot / ticket not pending             */
   UBU_SW_ERR_NOMEM = -7,
   UBU_SW_ERR_CAPACITY = -8      /* an output table / node bound was too small; the required count is written back */
 } ubu_sw_status;
 
-#define UBU_SW_MAX_READ   256u      /* rows handled by the packed 16-bit kernel (all BASELINE configs: 50..250 bp) */
-#define UBU_SW_MAX_WINDOW 65535u
+#define UBU_SW_MAX_READ   4096u     /* reads up to 256 bp run on the packed 16-bit kernels (all BASELINE configs: 50..250 bp); longer   */
+                                    /* ones (assembled contigs, Aligner.align's queries: 100 bp .. 2.5 kb) on the 32-bit warp-per-task    */
+                                    /* kernel, as long as read x window <= UBU_SW_MAX_LONG_CELLS                                          */
+#define UBU_SW_MAX_LONG_CELLS (1u << 26)
+#define UBU_SW_MAX_WINDOW 65535u    /* windows are regions / contigs, not chromosomes: lengths are 16-bit in ubu_sw_seqs                  */
 
 /* SPEC.md section 1. Defaults +1 / -3 / 5 / 2. Stands in for bwa's (implicit, default) scoring flags. */
 typedef struct { int32_t match, mismatch, gap_open, gap_ext; } ubu_sw_params;

@@ -568,3 +568,65 @@ def test_multi_gpu_driver_equals_one_call(aligner):
         assert rc == 0
         for f in FIELDS + ("cigar_n", "flags"):
             assert np.array_equal(res[f], one.results[f]), f
+
+
+# ---- reads longer than 256 bp: the contig-sized queries of Aligner.align (sw_long.cuh, 32-bit, a warp per task) ----------------
+def _mutated(rng, w, L):
+    s = int(rng.integers(0, max(len(w) - L, 1)))
+    r = list(w[s:s + L]) + list(rng.choice(list("ACGT"), size=max(0, L - len(w[s:s + L]))))
+    k = 0
+    while k < len(r):
+        u = rng.random()
+        if u < 0.02: r[k] = "ACGT"[int(rng.integers(0, 4))]
+        elif u < 0.025: r[k:k] = list(rng.choice(list("ACGT"), size=int(rng.integers(1, 30))))
+        elif u < 0.03: del r[k:k + int(rng.integers(1, 30))]
+        k += 1
+    return "".join(r[:L]) or "A"
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_long_reads_randomized_differential(seed):
+    """Contig-sized queries (257 .. 2500 bp) mixed with short reads in one batch, random scoring, N, shared windows:
+    every record and CIGAR against the oracle."""
+    rng = np.random.default_rng(3000 + seed)
+    params = [(1, -3, 5, 2), (2, -1, 3, 1), (5, -4, 10, 1), (1, -1, 0, 1)][seed]
+    alphabet = list("ACGT") if seed % 2 else list("ACGTN")
+    pw = None if seed % 2 else [0.2475, 0.2475, 0.2475, 0.2475, 0.01]
+    wins = ["".join(rng.choice(alphabet, size=int(rng.integers(300, 4000)), p=pw)) for _ in range(12)]
+    reads, idx = [], []
+    for k in range(90):
+        wi = int(rng.integers(0, len(wins)))
+        L = int(rng.choice([int(rng.integers(257, 2501)), int(rng.integers(1, 257)), 257, 2500, 512, 1024]))
+        reads.append(_mutated(rng, wins[wi], L)); idx.append(wi)
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    idx = np.array(idx, dtype=np.uint32)
+    with U.SwAligner(*params) as a:
+        al = a.align(rs, ws, idx)
+    check_against_oracle(al, rs, ws, idx, params)
+    assert max(len(r) for r in reads) > 2000
+
+
+def test_long_reads_edge_cases(aligner):
+    """Longest read the library takes (4096), a long read against a short window, a long homopolymer (every tie), a long read
+    that does not align at all, and a batch made only of long reads."""
+    rng = np.random.default_rng(77)
+    w = "".join(rng.choice(list("ACGT"), size=6000))
+    reads = [w[100:4196], "".join(rng.choice(list("ACGT"), size=700)), "A" * 600, "C" * 300, w[2000:2300] + "TTTT" + w[2300:2700]]
+    wins = [w, w[3000:3100], "A" * 900, "G" * 500, w]
+    rs, ws = U.pack_texts(reads), U.pack_texts(wins)
+    al = aligner.align(rs, ws)
+    check_against_oracle(al, rs, ws, None)
+    assert al.cigar_string(0) == "4096M" and int(al.results[3]["flags"]) & 1 and "4I" in al.cigar_string(4)
+
+
+def test_extreme_scoring_with_long_reads():
+    """match 31: scores far beyond 16 bits' comfort (31 x 2000 = 62000) only exist on the 32-bit long-read path."""
+    rng = np.random.default_rng(6)
+    w = "".join(rng.choice(list("ACGT"), size=3000))
+    reads = [w[500:2500], _mutated(rng, w, 1500), "A" * 300]
+    r, ws = U.pack_texts(reads), U.pack_texts([w, w, "C" * 100 + "A" * 40 + "C" * 100])
+    params = (31, -64, 63, 31)
+    with U.SwAligner(*params) as a:
+        al = a.align(r, ws)
+    check_against_oracle(al, r, ws, None, params)
+    assert int(al.results[0]["score"]) == 31 * 2000

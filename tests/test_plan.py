@@ -16,7 +16,7 @@ def plan(reads, wins, idx):
     n = reads.count
     rs, ws = reads.as_struct(), wins.as_struct()
     ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32)
-    order = np.zeros(n + 64, dtype=np.uint32)
+    order = np.zeros(n + 128, dtype=np.uint32)
     launches = np.zeros((64, 6), dtype=np.int32)
     n_slots, ident, nl = C.c_uint32(0), C.c_int(0), C.c_int(0)
     rc = N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), None if ix is None else ix.ctypes.data, order.ctypes.data, order.shape[0],
@@ -29,13 +29,17 @@ def check_invariants(reads, wins, idx, order, launches):
     n = reads.count
     real = order[order != PAD]
     assert np.array_equal(np.sort(real), np.arange(n, dtype=np.uint32))            # every task exactly once
-    assert order.shape[0] % 2 == 0 and order.shape[0] - n <= 2 * max(len(launches), 1)
+    n_long = sum(int(l[3]) for l in launches if l[0] == -1)
+    assert (order.shape[0] - n_long) % 2 == 0 and order.shape[0] - n <= 2 * max(len(launches), 1)
     covered = np.zeros(order.shape[0], dtype=np.int32)
     win_of = (lambda t: int(idx[t])) if idx is not None else (lambda t: int(t))
     for rows, has_n, first, slots, wmax, shared in launches:
-        assert slots % 2 == 0 and slots > 0
         covered[first:first + slots] += 1
         part = order[first:first + slots]
+        if rows == -1:                                                             # the long-read kernel's list: reads beyond 256 bp, no padding
+            assert first + slots == order.shape[0] and np.all(part != PAD) and all(int(reads.len[t]) > 256 for t in part)
+            continue
+        assert slots % 2 == 0 and slots > 0
         for t in part[part != PAD]:
             assert int(reads.len[t]) <= rows
             assert int(wins.len[win_of(t)]) <= wmax
@@ -100,9 +104,27 @@ def test_plan_rejects_bad_batches_and_handles_empty_ones():
     bad = np.array([0, 1], dtype=np.uint32)                                         # window index out of range
     assert N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), bad.ctypes.data, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_ARG
     assert N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_ARG   # counts differ
-    long_read = U.pack_texts(["A" * 300])
-    ls = long_read.as_struct()
-    assert N.lib().ubu_sw_debug_plan(C.byref(ls), C.byref(ws), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_TOO_LONG
+    w1s = U.pack_texts(["ACGTACGT"]); w1 = w1s.as_struct()
+    for text, want in (("A" * 300, 0), ("A" * 4096, 0), ("A" * 4097, N.ERR_TOO_LONG)):      # reads beyond 256 bp go to the long-read kernel, up to 4096
+        lr = U.pack_texts([text]); ls = lr.as_struct()
+        assert N.lib().ubu_sw_debug_plan(C.byref(ls), C.byref(w1), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == want
+    bws = U.pack_texts(["ACGT" * 16000]); big_w = bws.as_struct()                 # 4096 x 64000 cells > 2^26: too large a matrix
+    lr = U.pack_texts(["A" * 4096]); ls = lr.as_struct()
+    assert N.lib().ubu_sw_debug_plan(C.byref(ls), C.byref(big_w), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_TOO_LONG
+
+
+def test_long_reads_get_their_own_list_behind_the_slots():
+    rng = np.random.default_rng(5)
+    lens = [100, 300, 76, 2500, 250, 257, 150, 1024]
+    reads = U.pack_texts(["".join(rng.choice(list("ACGT"), size=L)) for L in lens])
+    wins = U.pack_texts(["".join(rng.choice(list("ACGT"), size=3000)) for _ in lens])
+    order, ident, launches = plan(reads, wins, None)
+    assert not ident and launches[-1][0] == -1 and launches[-1][3] == 4
+    assert sorted(int(t) for t in order[-4:]) == [1, 3, 5, 7]
+    check_invariants(reads, wins, None, order, launches)
+    only_long = U.pack_texts(["".join(rng.choice(list("ACGT"), size=400)) for _ in range(3)])
+    order, ident, launches = plan(only_long, U.pack_texts(["ACGT" * 200] * 3), None)
+    assert len(launches) == 1 and launches[0][0] == -1 and order.shape[0] == 3
 
 
 def test_mixed_read_lengths_in_one_class_with_exactly_sized_buffers():

@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("UBU_SW_LIB") or os.path.join(HERE, "libubu_sw.so")   
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_CIGAR_POOL, ERR_TOO_LONG, ERR_NO_DEVICE, ERR_BUSY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 FLAG_UNALIGNED = 1
-MAX_READ = 256
+MAX_READ = 4096
+MAX_LONG_CELLS = 1 << 26
 MAX_WINDOW = 65535
 
 

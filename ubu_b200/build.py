@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 UNITS = {
-    "ubu_sw.cu": ["sw_common.cuh", "sw_fwd16.cuh", "sw_fwd16s.cuh", "sw_tb.cuh", "sw_tbstrip.cuh", "sw_post.cuh"],
+    "ubu_sw.cu": ["sw_common.cuh", "sw_fwd16.cuh", "sw_fwd16s.cuh", "sw_tb.cuh", "sw_tbstrip.cuh", "sw_long.cuh", "sw_post.cuh"],
     "ubu_kmer.cu": ["sw_common.cuh"],
     "ubu_pack.cu": [],
 }

@@ -6,6 +6,7 @@
 #include "sw_fwd16s.cuh"
 #include "sw_tb.cuh"
 #include "sw_tbstrip.cuh"
+#include "sw_long.cuh"
 #include "sw_post.cuh"
 
 #include <algorithm>
@@ -107,6 +108,8 @@ struct Slot {
   size_t bias_rp = 0, bias_rn = 0, bias_wp = 0, bias_wn = 0; uint32_t bias_w = 0;
   PinBuf<unsigned int> h_ctr;
   std::vector<FwdLaunch> launches;
+  std::vector<uint32_t> long_tasks;      // reads beyond the packed classes (L > 256): sw_long_kernel, one warp per task
+  DevBuf<unsigned char> d_long; size_t long_per_warp = 0; int long_grid = 0;
   std::vector<uint32_t> tmp_keys, tmp_end, plain_order;     // plain_order: the order array when planning without a device
   // staged batch
   bool staged = false, ran = false, pending = false;
@@ -325,8 +328,9 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       win_n = any != 0;
     }
     const int c0 = cfg_of_len(lmin), c1 = cfg_of_len(lmax);
-    if (n && wins->count && c1 < 0) return UBU_SW_ERR_TOO_LONG;
-    if (n && wins->count && c0 == c1 && wmin == wmax && !win_n) {
+    if (n && wins->count && lmax > LONG_MAX_READ) return UBU_SW_ERR_TOO_LONG;
+    s.long_tasks.clear();
+    if (n && wins->count && c1 >= 0 && c0 == c1 && wmin == wmax && !win_n) {
       uint32_t bad = 0, imax = 0;
       const uint32_t wbytes = ((uint32_t)wmax + 3u) / 4u;
       if (!trusted) {
@@ -416,8 +420,13 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
       if (reads->nmask && (uint64_t)reads->nmask_off[t] + ((uint32_t)L + 7u) / 8u > reads->nmask_bytes) return UBU_SW_ERR_ARG;
     }
     const int c = cfg_of_len(L);
-    if (c < 0) return UBU_SW_ERR_TOO_LONG;
     const int W = wins->len[ri];
+    if (c < 0) {                          // a contig-sized query: its own kernel, outside the length classes
+      if ((uint32_t)L > LONG_MAX_READ || (uint64_t)L * (uint64_t)W > LONG_MAX_CELLS) return UBU_SW_ERR_TOO_LONG;
+      s.long_tasks.push_back(t);
+      s.tmp_keys[t] = 0xFFFFFFFFu;
+      continue;
+    }
     const int b = c * 2 + (wins->nmask && win_has_n[ri] ? 1 : 0);
     ++cnt[b];
     wmin[b] = std::min(wmin[b], W); wmaxv[b] = std::max(wmaxv[b], W);
@@ -430,12 +439,13 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
   uint32_t start[NB + 1]; start[0] = 0;
   for (int b = 0; b < NB; ++b) start[b + 1] = start[b] + ((cnt[b] + 1u) & ~1u);
   s.n_slots = start[NB];
-  if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots, 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
-  else s.plain_order.assign(std::max<size_t>(s.n_slots, 2), 0u);
+  if (h) { cudaError_t e = s.h_order.reserve(std::max<size_t>(s.n_slots + s.long_tasks.size(), 2)); if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(order)"); }
+  else s.plain_order.assign(std::max<size_t>(s.n_slots + s.long_tasks.size(), 2), 0u);
   uint32_t* order = h ? s.h_order.p : s.plain_order.data();
+  std::copy(s.long_tasks.begin(), s.long_tasks.end(), order + s.n_slots);          // the long tasks follow the slots
   uint32_t fill[NB];
   for (int b = 0; b < NB; ++b) fill[b] = start[b];
-  for (uint32_t t = 0; t < n; ++t) order[fill[s.tmp_keys[t] >> 16]++] = t;
+  for (uint32_t t = 0; t < n; ++t) if (s.tmp_keys[t] != 0xFFFFFFFFu) order[fill[s.tmp_keys[t] >> 16]++] = t;
   for (int b = 0; b < NB; ++b) if (cnt[b] & 1u) order[fill[b]] = 0xFFFFFFFFu;
 
   // inside a bucket, order by window length when it varies (so a pair / a warp sweeps similar widths)
@@ -526,7 +536,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   if (s.reads_n) { CU(h, s.d_rn.reserve(rn_bytes + 16)); CU(h, s.d_rnoff.reserve(n)); }
   if (s.wins_n) { CU(h, s.d_wn.reserve(wn_bytes + 16)); CU(h, s.d_wnoff.reserve(nw)); }
   if (idx) CU(h, s.d_idx.reserve(n));
-  CU(h, s.d_order.reserve(s.n_slots)); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
+  CU(h, s.d_order.reserve(s.n_slots + s.long_tasks.size())); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
   CU(h, s.d_fwd.reserve(n)); CU(h, s.d_res.reserve(n));
   CU(h, s.d_ctr.reserve(64)); CU(h, s.h_ctr.reserve(16));
   if (s.cig_cap < 6u * n + 4096u) { s.cig_cap = 6u * n + 4096u; }
@@ -582,6 +592,20 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     }
   }
 
+  s.long_grid = 0;
+  if (!s.long_tasks.empty()) {            // contig-sized queries: per-warp scratch sized for the largest of them, a warp per task
+    size_t per = 0;
+    for (uint32_t t : s.long_tasks) {
+      const uint32_t ri = idx ? idx[t] - (bias ? bias->w : 0u) : t;
+      per = std::max(per, long_scratch_bytes(reads->len[t], wins->len[ri]));
+    }
+    per = (per + 255) & ~(size_t)255;
+    const size_t warps_per_cta = LONG_THREADS / 32;
+    size_t ctas = std::min<size_t>((s.long_tasks.size() + warps_per_cta - 1) / warps_per_cta, (size_t)h->sm_count * 2);
+    ctas = std::max<size_t>(1, std::min<size_t>(ctas, ((size_t)4 << 30) / (per * warps_per_cta)));
+    s.long_per_warp = per; s.long_grid = (int)ctas;
+    CU(h, s.d_long.reserve(ctas * warps_per_cta * per + 256));
+  }
   cudaStream_t st = s.stream;
   CU(h, cudaMemcpyAsync(s.d_rp.p, reads->packed + r_lo, r_bytes, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(s.d_roff.p, reads->off, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
@@ -598,7 +622,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     CU(h, cudaMemcpyAsync(s.d_wnoff.p, wins->nmask_off, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
   }
   if (idx) CU(h, cudaMemcpyAsync(s.d_idx.p, idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-  if (!s.identity_order) CU(h, cudaMemcpyAsync(s.d_order.p, s.h_order.p, sizeof(uint32_t) * s.n_slots, cudaMemcpyHostToDevice, st));
+  if (!s.identity_order) CU(h, cudaMemcpyAsync(s.d_order.p, s.h_order.p, sizeof(uint32_t) * (s.n_slots + s.long_tasks.size()), cudaMemcpyHostToDevice, st));
   s.staged = true;
   return UBU_SW_OK;
 }
@@ -682,6 +706,14 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[1]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
                                                           s.d_wide.p, max_rows, s.bw_cap);
   CU(h, cudaGetLastError()); ++s.n_launches;
+  if (s.long_grid > 0) {                              // contig-sized queries (L > 256): forward, direction matrix and walk in one kernel
+    LongArgs la;
+    la.list = s.d_order.p + s.n_slots; la.n = (uint32_t)s.long_tasks.size(); la.work = s.d_ctr.p + CTR_WORK + 2;
+    la.scratch = s.d_long.p; la.per_warp = s.long_per_warp;
+    if (s.any_n) sw_long_kernel<true><<<s.long_grid, LONG_THREADS, 0, ax[0]>>>(a, la);
+    else sw_long_kernel<false><<<s.long_grid, LONG_THREADS, 0, ax[0]>>>(a, la);
+    CU(h, cudaGetLastError()); ++s.n_launches;
+  }
   for (int k = 0; k < kAux; ++k) {                    // join
     CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
     CU(h, cudaStreamWaitEvent(st, s.ev_join[k], 0));
@@ -815,7 +847,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     s.d_rp.release(); s.d_rn.release(); s.d_wp.release(); s.d_wn.release();
     s.d_roff.release(); s.d_rnoff.release(); s.d_woff.release(); s.d_wnoff.release(); s.d_idx.release();
     s.d_order.release(); s.d_lists.release(); s.d_cig.release(); s.d_rlen.release(); s.d_wlen.release();
-    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_strip.release(); s.d_wide.release(); s.d_gsel.release();
+    s.d_fwd.release(); s.d_res.release(); s.d_ctr.release(); s.d_hstore.release(); s.d_strip.release(); s.d_long.release(); s.d_wide.release(); s.d_gsel.release();
     s.h_order.release(); s.h_ctr.release();
     s.h_pool.release();
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
@@ -1421,14 +1453,19 @@ int ubu_sw_debug_plan(const ubu_sw_seqs* reads, const ubu_sw_seqs* windows, cons
   if (identity) *identity = 0;
   if (reads->count == 0) return UBU_SW_OK;
   rc = plan_batch(nullptr, s, reads, windows, pair_ref_idx); if (rc) return rc;
-  *n_slots = s.n_slots; *n_launches = (int)s.launches.size();
+  const uint32_t n_long = (uint32_t)s.long_tasks.size();
+  *n_slots = s.n_slots + n_long; *n_launches = (int)s.launches.size() + (n_long ? 1 : 0);
   if (identity) *identity = s.identity_order ? 1 : 0;
   if (order_out) {
-    if (order_cap < s.n_slots) return UBU_SW_ERR_CAPACITY;
-    for (uint32_t k = 0; k < s.n_slots; ++k) order_out[k] = s.identity_order ? (k < reads->count ? k : 0xFFFFFFFFu) : s.plain_order[k];
+    if (order_cap < s.n_slots + n_long) return UBU_SW_ERR_CAPACITY;
+    for (uint32_t k = 0; k < s.n_slots + n_long; ++k) order_out[k] = s.identity_order ? (k < reads->count ? k : 0xFFFFFFFFu) : s.plain_order[k];
   }
   if (launches_out) {
-    if (launches_cap < (int)s.launches.size()) return UBU_SW_ERR_CAPACITY;
+    if (launches_cap < *n_launches) return UBU_SW_ERR_CAPACITY;
+    if (n_long) {                      // the long tasks (sw_long_kernel) follow the slots: rows = -1 marks the entry
+      int32_t* o = launches_out + 6 * s.launches.size();
+      o[0] = -1; o[1] = 0; o[2] = (int32_t)s.n_slots; o[3] = (int32_t)n_long; o[4] = 0; o[5] = 0;
+    }
     for (size_t k = 0; k < s.launches.size(); ++k) {
       const FwdLaunch& L = s.launches[k];
       int32_t* o = launches_out + 6 * k;
