@@ -91,6 +91,26 @@ __device__ __forceinline__ uint32_t load16n(const uint8_t* __restrict__ nm, int 
   return adj >= 16 ? 0u : ((v << adj) & 0xFFFFu);
 }
 
+// bit u of a 16-bit mask -> bit 2u (the position of base u's low code bit in a load16 word)
+__device__ __forceinline__ uint32_t spread16(uint32_t m) {
+  m = (m | (m << 8)) & 0x00FF00FFu;
+  m = (m | (m << 4)) & 0x0F0F0F0Fu;
+  m = (m | (m << 2)) & 0x33333333u;
+  return (m | (m << 1)) & 0x55555555u;
+}
+// mismatching, N-free columns among the `len` (<= 16) bases starting at read position qi / window position rj (0-based)
+__device__ __forceinline__ int mismatches16(const uint8_t* __restrict__ q, const uint8_t* __restrict__ r, const uint8_t* __restrict__ qn,
+                                            const uint8_t* __restrict__ rn, int qi, int rj, int len) {
+  uint32_t x = load16(q, qi) ^ load16(r, rj);
+  x = (x | (x >> 1)) & 0x55555555u;
+  uint32_t nm = 0u;
+  if (qn) nm |= load16n(qn, qi);
+  if (rn) nm |= load16n(rn, rj);
+  x &= ~spread16(nm);
+  if (len < 16) x &= (1u << (2 * len)) - 1u;
+  return __popc(x);
+}
+
 // prmt.b32 in its default mode: selector nibble bit 3 set = replicate the selected byte's sign bit.
 // (Inline PTX rather than __byte_perm, whose documented contract only covers selector bits 2:0.)
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {

@@ -232,11 +232,8 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
     int qi = i, rj = j;                                     // 0-based positions of the first aligned bases
     for (int k = o.n - 1; k >= 0; --k) {
       const int len = (int)(o.ops[k] >> 4); const uint32_t op = o.ops[k] & 15u;
-      if (op == UBU_SW_CIGAR_M) {
-        for (int u = 0; u < len; ++u) {
-          const bool isn = (t.qn && nbit(t.qn, (uint32_t)(qi + u))) || (t.rn && nbit(t.rn, (uint32_t)(rj + u)));
-          if (!isn && base2(t.q, (uint32_t)(qi + u)) != base2(t.r, (uint32_t)(rj + u))) ++mism;
-        }
+      if (op == UBU_SW_CIGAR_M) {                           // 16 columns per XOR + popcount
+        for (int u = 0; u < len; u += 16) mism += mismatches16(t.q, t.r, t.qn, t.rn, qi + u, rj + u, min(16, len - u));
         qi += len; rj += len;
       } else if (op == UBU_SW_CIGAR_I) qi += len;
       else if (op == UBU_SW_CIGAR_D) rj += len;
@@ -276,10 +273,7 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
           uint32_t nm = 0u;
           if (t.qn) nm |= load16n(t.qn, i - 16);
           if (t.rn) nm |= load16n(t.rn, je - 16);
-          uint32_t spread = 0u;                                 // bit u of nm -> bit 2u
-#pragma unroll
-          for (int u = 0; u < 16; ++u) spread |= ((nm >> u) & 1u) << (2 * u);
-          x &= ~spread;
+          x &= ~spread16(nm);
         }
         const int d = __popc(x);
         keep = (16 - d) * ma + d * mm + (maxk - 16) * ma >= S;
@@ -304,11 +298,7 @@ tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* 
         if (run + rem * ma < S) {                               // S is out of reach inside this word: take it in one step
           const uint32_t fields = rem == 16 ? 0x55555555u : (0x55555555u << (2 * (16 - rem)));
           uint32_t dbits = (x | (x >> 1)) & fields, nbits = 0u;
-          if (HAS_N) {
-#pragma unroll
-            for (int u = 0; u < 16; ++u) nbits |= ((nm >> u) & 1u) << (2 * u);
-            nbits &= fields; dbits &= ~nbits;
-          }
+          if (HAS_N) { nbits = spread16(nm) & fields; dbits &= ~nbits; }
           const int d = __popc(dbits), nn = __popc(nbits);
           run += (rem - d - nn) * ma + d * mm; mism += d;
           if (run + (maxk - k0 - rem) * ma < S) done = true;
