@@ -17,6 +17,10 @@ def pytest_configure(config):
 
         if not os.path.exists(B.LIB):
             B.build()
+        if not os.path.exists(os.path.join(ROOT, "host", "libubu_host.so")):
+            import __graft_entry__ as G
+
+            G.build()
     except Exception as e:  # the ABI tests will then fail loudly with the loader's message
         sys.stderr.write(f"[conftest] could not build libubu_sw.so: {e}\n")
 
