@@ -368,6 +368,7 @@ def main():
         dist = dist_
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")      # host-side waits: an NCCL barrier spins on the waiting ranks' GPUs
     else:
         torch.cuda.set_device(local)
 
@@ -570,8 +571,9 @@ def main():
     al.close()
     del flush
     torch.cuda.empty_cache()
+    torch.cuda.synchronize()
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=host_group)              # every rank's GPU is idle from here on: rank 0 drives all of them in the multi leg
     if rank == 0 and not args.no_multi and hasattr(N.lib(), "ubu_sw_multi_create"):
         try:
             line["multi"] = multi_leg(world, args.multi_reads, max(2, min(args.steps, 4)), 1, threads)
@@ -580,7 +582,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
     return 0
 
