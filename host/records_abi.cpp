@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../include/ubu_records.h"
+#include "aligner.hpp"
 #include "records.hpp"
 
 namespace {
@@ -73,6 +74,18 @@ int ubu_rec_align_and_clean_contigs(const char* reference_fasta, int num_threads
 int ubu_rec_align_to_contigs(int num_threads, int device, const char* temp_dir, const char* input_sam, const char* aligned, const char* contig_fasta) {
   if (!temp_dir || !input_sam || !aligned || !contig_fasta) return UBU_REC_ERR_ARG;
   return guarded([&] { ubu::ReAligner r("", num_threads, 100, device); r.alignToContigs(temp_dir, input_sam, aligned, contig_fasta); return UBU_REC_OK; });
+}
+int ubu_aligner_align(const char* reference_fasta, int num_threads, int device, const char* input, const char* output_sam) {
+  if (!reference_fasta || !input || !output_sam) return UBU_REC_ERR_ARG;
+  return guarded([&] { ubu::Aligner a(reference_fasta, num_threads, device); a.align(input, output_sam); return UBU_REC_OK; });
+}
+int ubu_aligner_short_align(const char* reference_fasta, int num_threads, int device, const char* input, const char* output_sam) {
+  if (!reference_fasta || !input || !output_sam) return UBU_REC_ERR_ARG;
+  return guarded([&] { ubu::Aligner a(reference_fasta, num_threads, device); a.shortAlign(input, output_sam); return UBU_REC_OK; });
+}
+int ubu_aligner_index(const char* reference_fasta) {
+  if (!reference_fasta) return UBU_REC_ERR_ARG;
+  return guarded([&] { ubu::Aligner a(reference_fasta, 1); a.index(); return UBU_REC_OK; });
 }
 void ubu_rec_free(char* p) { free(p); }
 const char* ubu_rec_last_error(void) { return g_err.c_str(); }

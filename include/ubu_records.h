@@ -43,6 +43,12 @@ int ubu_rec_align_and_clean_contigs(const char* reference_fasta, int num_threads
                                     const char* temp_dir, int should_remove_soft_clips, char** clean_fasta_out);
 int ubu_rec_align_to_contigs(int num_threads, int device, const char* temp_dir, const char* input_sam, const char* aligned_to_contig_sam,
                              const char* contig_fasta);
+/* The aligner facade itself, path in / path out like the reference (assembly/Aligner.java:13-16, 18-22, 46-56, 62-69): every read of `input`
+ * (FASTA / FASTQ) against every sequence of `reference_fasta` on the GPU, SAM with NM XM X0 X1 XA written to `output_sam`.
+ * A failure returns UBU_REC_ERR_ALIGNER where the reference throws RuntimeException("BWA exited with non-zero return code"). */
+int ubu_aligner_align(const char* reference_fasta, int num_threads, int device, const char* input, const char* output_sam);
+int ubu_aligner_short_align(const char* reference_fasta, int num_threads, int device, const char* input, const char* output_sam);
+int ubu_aligner_index(const char* reference_fasta);
 void ubu_rec_free(char* p);
 const char* ubu_rec_last_error(void);
 

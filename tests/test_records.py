@@ -292,7 +292,8 @@ def test_records_library_exports_every_symbol_of_the_header():
         assert name in hdr
         getattr(l, name)
     import re
-    assert set(re.findall(r"\b(ubu_rec_[a-z0-9_]+)\s*\(", hdr)) == set(R.SYMBOLS)
+    assert set(re.findall(r"\b(ubu_(?:rec|aligner)_[a-z0-9_]+)\s*\(", hdr)) == set(R.SYMBOLS)
+    assert R.lib().ubu_aligner_index(b"/nonexistent/ref.fa") == R.ERR_ALIGNER        # the reference throws RuntimeException (Aligner.java:41-43)
 
 
 # ---- composites on the GPU: alignAndCleanContigs -> alignToContigs -> adjustReads --------------------------------------------------

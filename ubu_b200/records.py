@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(HERE), "host", "libubu_host.so")
 OK, ERR_ARG, ERR_STATE, ERR_IO, ERR_ALIGNER = 0, -1, -2, -3, -4
 SYMBOLS = ["ubu_rec_combine_chimera", "ubu_rec_clean_contigs", "ubu_rec_adjust_reads", "ubu_rec_update_read_alignment", "ubu_rec_sam2fastq",
-           "ubu_rec_sam2fastq_paired", "ubu_rec_align_and_clean_contigs", "ubu_rec_align_to_contigs", "ubu_rec_free", "ubu_rec_last_error"]
+           "ubu_rec_sam2fastq_paired", "ubu_rec_align_and_clean_contigs", "ubu_rec_align_to_contigs", "ubu_rec_free", "ubu_rec_last_error",
+           "ubu_aligner_align", "ubu_aligner_short_align", "ubu_aligner_index"]
 _lib = None
 
 
@@ -103,3 +104,9 @@ def align_and_clean_contigs(reference_fasta: str, contig_fasta: str, temp_dir: s
 
 def align_to_contigs(temp_dir: str, input_sam: str, aligned_to_contig_sam: str, contig_fasta: str, num_threads: int = 1, device: int = 0) -> None:
     _check(lib().ubu_rec_align_to_contigs(num_threads, device, temp_dir.encode(), input_sam.encode(), aligned_to_contig_sam.encode(), contig_fasta.encode()))
+
+
+def aligner_align(reference_fasta: str, input_path: str, output_sam: str, short: bool = False, num_threads: int = 1, device: int = 0) -> None:
+    """Aligner.align / Aligner.shortAlign (Aligner.java:18-22, 46-56) through the C ABI a JNI caller binds."""
+    fn = lib().ubu_aligner_short_align if short else lib().ubu_aligner_align
+    _check(fn(reference_fasta.encode(), num_threads, device, input_path.encode(), output_sam.encode()))
