@@ -221,6 +221,25 @@ def packing_leg(w, threads: int):
     return out
 
 
+def java_baseline(n_reads: int, threads: int) -> dict:
+    """baseline/SwOracle.java (a line-for-line Java restatement of SPEC.md) run iff a JDK is on PATH."""
+    import shutil
+
+    if not (shutil.which("java") and shutil.which("javac")):
+        return {"status": "Java baseline not run: no JVM on this box"}
+    try:
+        cls = os.path.join(ROOT, "baseline", "_classes")
+        os.makedirs(cls, exist_ok=True)
+        subprocess.run(["javac", "-d", cls, os.path.join(ROOT, "baseline", "SwOracle.java")], check=True, capture_output=True, timeout=120)
+        out = subprocess.run(["java", "-Xmx8g", "-cp", cls, "SwOracle", str(n_reads), str(READ_LEN), str(WIN_LEN), str(threads), "1003"],
+                             check=True, capture_output=True, text=True, timeout=600).stdout
+        d = json.loads(out.strip().split("\n")[-1])
+        d["status"] = "SPEC oracle (Java), NOT a reference aligner (none exists)"
+        return d
+    except Exception as e:
+        return {"status": f"Java baseline failed: {e!r}"}
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -564,6 +583,7 @@ def main():
                                           "(oracle/sw_oracle.c, full-matrix 32-bit + traceback); NOT a reference Java aligner (none exists)",
                                 "gpu_results_match_on_sample": bool(agree)}
         line["packing"] = packing_leg(w, threads)
+        line["java_baseline"] = java_baseline(min(args.cpu_sample, 100_000), threads)
     del res0
     if rank == 0 and world == 1 and not args.no_configs:
         del w
