@@ -209,6 +209,8 @@ typedef struct {
   const uint32_t*    pair_ref_idx;   /* window of every read (NULL = read k <-> window k) */
   const char* const* rnames;         /* per window, NULL = "w<index>" */
   const int64_t*     window_pos0;    /* 0-based start of every window on its reference sequence, NULL = 0 */
+  uint64_t           cigar_pool_n;   /* ops readable at cigar_pool; a record whose slice leaves the pool fails the call with UBU_SW_ERR_ARG
+                                      * (0 = unknown: slices are not checked) */
 } ubu_sw_sam_names;
 /* Formats on `threads` host threads (0 = all cores) and writes the blocks to file descriptor fd in order (fd < 0: format only). */
 int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_result* res, const uint32_t* cigar_pool, uint32_t n,

@@ -174,6 +174,13 @@ def test_sam_writer_formats_records_in_input_order(tmp_path):
         text = path.read_text()
         assert nbytes == len(text.encode()) and text.split("\n")[:-1] == want
     assert U.write_sam(-1, reads, al, idx, first_index=1000, qname_prefix="q", window_pos0=pos0) == nbytes      # format only
+    # a record whose CIGAR slice leaves the pool is an argument error, not a wild read (ubu_sw_sam_names.cigar_pool_n)
+    bad = U.Alignments(al.results.copy(), al.cigar_pool.copy())
+    k = int(np.nonzero(bad.results["cigar_n"] > 0)[0][0])
+    bad.results["cigar_off"][k] = bad.cigar_pool.shape[0]
+    with pytest.raises(U.UbuSwError) as e:
+        U.write_sam(-1, reads, bad, idx)
+    assert e.value.status == N.ERR_ARG
 
 
 def test_jni_shim_parses_against_the_c_abi():

@@ -45,7 +45,7 @@ class Refs(C.Structure):
 
 class SamNames(C.Structure):
     _fields_ = [("qname_prefix", C.c_char_p), ("first_index", C.c_uint64), ("pair_ref_idx", C.c_void_p), ("rnames", C.c_void_p),
-                ("window_pos0", C.c_void_p)]
+                ("window_pos0", C.c_void_p), ("cigar_pool_n", C.c_uint64)]
 
 
 class KmerParams(C.Structure):

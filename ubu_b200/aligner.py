@@ -198,11 +198,11 @@ def write_sam(fd: int, reads: SeqSet, al: Alignments, pair_ref_idx: Optional[np.
     n = len(al)
     idx = None if pair_ref_idx is None else np.ascontiguousarray(pair_ref_idx, dtype=np.uint32)
     pos0 = None if window_pos0 is None else np.ascontiguousarray(window_pos0, dtype=np.int64)
+    pool = np.ascontiguousarray(al.cigar_pool, dtype=np.uint32)
     names = N.SamNames(qname_prefix.encode("ascii"), first_index, None if idx is None else idx.ctypes.data, None,
-                       None if pos0 is None else pos0.ctypes.data)
+                       None if pos0 is None else pos0.ctypes.data, int(pool.shape[0]))
     rs = reads.as_struct()
     res = np.ascontiguousarray(al.results)
-    pool = np.ascontiguousarray(al.cigar_pool, dtype=np.uint32)
     out = C.c_uint64(0)
     rc = N.lib().ubu_sw_sam_write(fd, C.byref(rs), res.ctypes.data, pool.ctypes.data if pool.size else None, n, C.byref(names), threads,
                                   C.byref(out))

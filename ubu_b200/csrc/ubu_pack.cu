@@ -160,6 +160,7 @@ size_t ubu_sam_block(const ubu_sw_seqs* reads, const ubu_sw_result* res, const u
       *p++ = '\t';
       p = put_u(p, (uint64_t)((nm->window_pos0 ? nm->window_pos0[w] : 0) + (int64_t)r.ref_start)); *p++ = '\t';
       p = put_u(p, 37u); *p++ = '\t';
+      if (r.cigar_n && (!pool || (nm->cigar_pool_n && (uint64_t)r.cigar_off + r.cigar_n > nm->cigar_pool_n))) { out.clear(); return (size_t)-1; }   // slice outside the pool
       for (uint32_t c = 0; c < r.cigar_n; ++c) { const uint32_t op = pool[r.cigar_off + c]; p = put_u(p, op >> 4); *p++ = opc[(op & 15u) < 9 ? (op & 15u) : 0]; }
     }
     *p++ = '\t'; *p++ = '*'; *p++ = '\t'; *p++ = '0'; *p++ = '\t'; *p++ = '0'; *p++ = '\t';
@@ -198,6 +199,7 @@ extern "C" int ubu_sw_sam_write(int fd, const ubu_sw_seqs* reads, const ubu_sw_r
         pool.emplace_back([&, t] { const uint32_t lo = (b0 + t) * block, hi = std::min<uint32_t>(n, lo + block); used[t] = ubu_sam_block(reads, res, cigar_pool, lo, hi, names, bufs[t]); });
     } catch (...) { for (auto& th : pool) th.join(); return UBU_SW_ERR_NOMEM; }
     for (auto& th : pool) th.join();
+    for (unsigned t = 0; t < m; ++t) if (used[t] == (size_t)-1) return UBU_SW_ERR_ARG;          // a CIGAR slice outside the pool
     for (unsigned t = 0; t < m; ++t) {
       size_t off = 0;
       while (fd >= 0 && off < used[t]) { const ssize_t wr = write(fd, bufs[t].data() + off, used[t] - off); if (wr <= 0) return UBU_SW_ERR_ARG; off += (size_t)wr; }

@@ -1249,6 +1249,7 @@ int multi_align(ubu_sw_multi* m, const ubu_sw_seqs* reads, const ubu_sw_seqs* wi
         }
         const uint32_t lo = c * R.chunk, hi = (uint32_t)std::min<uint64_t>(n, (uint64_t)lo + R.chunk);
         blen[c % ring] = ubu_sam_block(reads, out, pool, lo, hi, names, bufs[c % ring]);
+        if (blen[c % ring] == (size_t)-1) { blen[c % ring] = 0; R.fail(UBU_SW_ERR_ARG); return; }
         formatted[c].store(1, std::memory_order_release);
         { std::lock_guard<std::mutex> lk(R.mu); }
         R.cv.notify_all();

@@ -81,7 +81,7 @@ class MultiAligner:
         if sam_fd is None:
             rc = self._lib.ubu_sw_multi_align(self._m, C.byref(rs), C.byref(ws), idx_p, res.ctypes.data, pool.ctypes.data, pool.shape[0], C.byref(used))
         else:
-            names = N.SamNames(qname_prefix.encode("ascii"), first_index, idx_p, None, None)
+            names = N.SamNames(qname_prefix.encode("ascii"), first_index, idx_p, None, None, int(pool.shape[0]))
             nbytes = C.c_uint64(0)
             rc = self._lib.ubu_sw_multi_align_sam(self._m, C.byref(rs), C.byref(ws), idx_p, res.ctypes.data, pool.ctypes.data, pool.shape[0],
                                                   C.byref(used), sam_fd, C.byref(names), sam_threads, C.byref(nbytes))
