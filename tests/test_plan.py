@@ -17,7 +17,7 @@ def plan(reads, wins, idx):
     rs, ws = reads.as_struct(), wins.as_struct()
     ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32)
     order = np.zeros(n + 128, dtype=np.uint32)
-    launches = np.zeros((64, 6), dtype=np.int32)
+    launches = np.zeros((512, 6), dtype=np.int32)
     n_slots, ident, nl = C.c_uint32(0), C.c_int(0), C.c_int(0)
     rc = N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), None if ix is None else ix.ctypes.data, order.ctypes.data, order.shape[0],
                                    C.byref(n_slots), C.byref(ident), launches.ctypes.data, launches.shape[0], C.byref(nl))
