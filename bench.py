@@ -240,6 +240,83 @@ def java_baseline(n_reads: int, threads: int) -> dict:
         return {"status": f"Java baseline failed: {e!r}"}
 
 
+def text_leg(al, w, U, N, threads: int, steps: int, n_reads: int, chunk: int, res_ref):
+    """End to end FROM TEXT: ASCII reads and windows in host memory -> 2-bit packing (ubu_sw_pack_batch on helper threads, into
+    pinned staging) -> ubu_sw_submit / ubu_sw_wait -> records in host memory; the packing of chunk c+1.. runs while chunk c is on
+    the GPU. Measured on the first n_reads reads of the step (same shape) to bound the text held in memory."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from ubu_b200 import sharding as SH
+
+    n = min(n_reads, w.n_tasks)
+    chars = np.frombuffer(b"ACTG", dtype=np.uint8)
+    idx_all = w.pair_ref_idx
+    bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+    L, W = READ_LEN, WIN_LEN
+    rb, wb = (L + 3) // 4, (W + 3) // 4
+    chunks = []
+    for lo, hi in bounds:                                     # the caller's text, chunk by chunk (reads and the windows they use)
+        w0, w1 = (int(idx_all[lo:hi].min()), int(idx_all[lo:hi].max()) + 1) if idx_all is not None else (lo, hi)
+        chunks.append({"lo": lo, "hi": hi, "w0": w0, "w1": w1,
+                       "rtext": np.ascontiguousarray(chars[unpack_uniform(w.reads, lo, hi)]).reshape(-1),
+                       "wtext": np.ascontiguousarray(chars[unpack_uniform(w.windows, w0, w1)]).reshape(-1),
+                       "idx": None if idx_all is None else np.ascontiguousarray(idx_all[lo:hi] - np.uint32(w0), dtype=np.uint32)})
+    max_m, max_w = max(c["hi"] - c["lo"] for c in chunks), max(c["w1"] - c["w0"] for c in chunks)
+    ring = al.slots + 2
+
+    def stage_set():
+        return {"rp": U.pinned_empty((max_m * rb,), np.uint8), "wp": U.pinned_empty((max_w * wb,), np.uint8),
+                "roff": (np.arange(max_m, dtype=np.int64) * rb).astype(np.uint32), "woff": (np.arange(max_w, dtype=np.int64) * wb).astype(np.uint32),
+                "rlen": np.full(max_m, L, dtype=np.uint16), "wlen": np.full(max_w, W, dtype=np.uint16),
+                "rtoff": np.arange(max_m, dtype=np.uint64) * np.uint64(L), "wtoff": np.arange(max_w, dtype=np.uint64) * np.uint64(W),
+                "pool": U.pinned_empty((6 * max_m + 4096,), np.uint32)}
+    stages = [stage_set() for _ in range(ring)]
+    res_p = U.pinned_empty((n,), U.RESULT_DTYPE)
+    pack_threads = max(1, threads // 2)
+    lib = N.lib()
+
+    def pack(ci, st):
+        c = chunks[ci]
+        m, mw = c["hi"] - c["lo"], c["w1"] - c["w0"]
+        cnt = C.c_uint32(0)
+        rc = lib.ubu_sw_pack_batch(c["rtext"].ctypes.data, st["rtoff"].ctypes.data, st["rlen"].ctypes.data, m, st["rp"].ctypes.data, st["roff"].ctypes.data,
+                                   None, None, pack_threads, C.byref(cnt))
+        rc |= lib.ubu_sw_pack_batch(c["wtext"].ctypes.data, st["wtoff"].ctypes.data, st["wlen"].ctypes.data, mw, st["wp"].ctypes.data, st["woff"].ctypes.data,
+                                    None, None, pack_threads, C.byref(cnt))
+        assert rc == 0
+        return (U.SeqSet(st["rp"][: m * rb], st["roff"][:m], st["rlen"][:m], None, None),
+                U.SeqSet(st["wp"][: mw * wb], st["woff"][:mw], st["wlen"][:mw], None, None))
+
+    def one_pass():
+        with ThreadPoolExecutor(max_workers=2) as ex:
+            futs = {ci: ex.submit(pack, ci, stages[ci % ring]) for ci in range(min(ring, len(chunks)))}
+            inflight = []
+            for ci, c in enumerate(chunks):
+                if len(inflight) == al.slots:
+                    t, done_ci = inflight.pop(0)
+                    al.wait(t)
+                    nxt = done_ci + ring                      # that chunk's staging set is free again
+                    if nxt < len(chunks):
+                        futs[nxt] = ex.submit(pack, nxt, stages[nxt % ring])
+                rs, ws = futs.pop(ci).result()
+                inflight.append((al.submit(rs, ws, c["idx"], res_p[c["lo"]:c["hi"]], stages[ci % ring]["pool"]), ci))
+            for t, _ in inflight:
+                al.wait(t)
+
+    one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / steps
+    same = all(np.array_equal(res_p[f], res_ref[f][:n]) for f in FIELDS + ("cigar_n",))
+    cells = float(n) * L * W
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "reads_per_s": n / dt, "ms": dt * 1e3, "reads": n,
+            "text_bytes_per_pass": int(sum(c["rtext"].size + c["wtext"].size for c in chunks)), "matches_device_resident_results": bool(same),
+            "how": f"ASCII text in host memory -> ubu_sw_pack_batch ({pack_threads} threads per call, two chunks being packed while earlier ones are "
+                   f"on the GPU) -> ubu_sw_submit/ubu_sw_wait over {len(chunks)} chunks of {chunk} reads -> records in pinned host memory; the first {n} "
+                   "reads of the step's workload"}
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -533,6 +610,11 @@ def main():
                            "how": "one ubu_sw_align_batch call per step on the whole pinned batch; chunking and slot pipeline inside the library",
                            "matches_device_resident_results": bool(same_q)}
         del whole_r, whole_w, whole_i, pool_q
+        if rank == 0 and world == 1:
+            try:
+                e2e["from_text"] = text_leg(al, w, U, N, threads, max(2, min(args.steps, 3)), 1_000_000, min(args.chunk, n), res0.results)
+            except Exception as e:
+                e2e["from_text"] = {"error": repr(e)}
 
     clocks = sampler.stop()
     # ---------------- roofline of the dominant kernel (forward pass) ----------------------------------
