@@ -105,7 +105,7 @@ void Aligner::run(const std::string& input, const std::string& outputSam) {
   if (!out) throw std::runtime_error("cannot write " + outputSam);
   out << "@HD\tVN:1.4\tSO:unsorted\n";
   for (const Rec& r : refs) out << "@SQ\tSN:" << r.name << "\tLN:" << r.seq.size() << "\n";
-  out << "@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md)\n";
+  out << "@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's\n";
   auto unmapped = [&](const Rec& rd) {
     out << rd.name << "\t4\t*\t0\t0\t*\t*\t0\t0\t" << rd.seq << "\t" << (rd.has_qual && !rd.qual.empty() ? rd.qual : "*") << "\n";
   };

@@ -225,6 +225,29 @@ bool updateReadAlignment(int contigPos, const std::vector<CigarElement>& contigC
   return true;
 }
 
+// ---- CompareToReference.numDifferences (CompareToReference.java:83-123) ---------------------------------------------------------------
+int numDifferences(const std::string& readBases, const std::string& refBases, int alignmentStart, const std::vector<CigarElement>& cigar) {
+  int diffs = 0; size_t readIdx = 0, refIdx = (size_t)(alignmentStart - 1);
+  for (const CigarElement& e : cigar) {
+    if (e.op == 'M') {
+      for (int i = 0; i < e.length; ++i) {
+        if (readIdx >= readBases.size() || refIdx >= refBases.size()) throw std::out_of_range("String index out of range");
+        const char a = (char)toupper((unsigned char)readBases[readIdx]), b = (char)toupper((unsigned char)refBases[refIdx]);
+        if (a != b && a != 'N' && b != 'N') ++diffs;                                             // :92
+        ++readIdx; ++refIdx;
+      }
+    } else if (e.op == 'I') readIdx += (size_t)e.length;
+    else if (e.op == 'D') refIdx += (size_t)e.length;
+    else if (e.op == 'S') readIdx += (size_t)e.length;                                           // N elements advance nothing (:99-108)
+  }
+  return diffs;
+}
+size_t countNonAcgtn(const std::string& bases) {
+  size_t n = 0;
+  for (unsigned char c : bases) { const char u = (char)toupper(c); if (u != 'A' && u != 'C' && u != 'G' && u != 'T' && u != 'N') ++n; }
+  return n;
+}
+
 // ---- CombineChimera3 ------------------------------------------------------------------------------------------------------------
 int CombineChimera3::getMappedReadStart(const SamRecord& read) {                                  // CombineChimera3.java:269-281
   for (const ReadBlock& b : ReadBlock::getReadBlocks(read.pos, read.cigar)) if (b.type != 'S') return b.readStart;

@@ -68,6 +68,13 @@ struct ReadBlock {
 bool updateReadAlignment(int contigPos, const std::vector<CigarElement>& contigCigar, int position, int readLength, int& newStart,
                          std::vector<CigarElement>& newCigar);
 
+// CompareToReference.numDifferences (assembly/CompareToReference.java:83-123), letter for letter: case-folded, 'N' on either side is never
+// a mismatch, every OTHER letter (IUPAC codes included) is compared as a letter. The device form (ubu_sw_recount_batch) works on 2-bit
+// codes and folds every non-ACGT letter into N, so it under-counts when a read or the reference holds IUPAC codes: callers route such
+// reads here (countNonAcgtn tells which).
+int numDifferences(const std::string& readBases, const std::string& refBases, int alignmentStart, const std::vector<CigarElement>& cigar);
+size_t countNonAcgtn(const std::string& bases);
+
 class CombineChimera3 {
  public:
   void combine(const std::string& input, const std::string& output);                         // files (SAM text)

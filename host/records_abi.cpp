@@ -55,6 +55,11 @@ int ubu_rec_update_read_alignment(int32_t contig_pos, const uint32_t* cc, uint32
     return UBU_REC_OK;
   });
 }
+int ubu_rec_num_differences(const char* read_bases, const char* ref_bases, int32_t alignment_start, const char* cigar, int32_t* diffs) {
+  if (!read_bases || !ref_bases || !cigar || !diffs) return UBU_REC_ERR_ARG;
+  return guarded([&] { *diffs = ubu::numDifferences(read_bases, ref_bases, alignment_start, ubu::parseCigar(cigar)); return UBU_REC_OK; });
+}
+uint64_t ubu_rec_count_non_acgtn(const char* bases) { return bases ? (uint64_t)ubu::countNonAcgtn(bases) : 0; }
 int ubu_rec_sam2fastq(const char* sam_in, char** fastq_out) {
   if (!sam_in || !fastq_out) return UBU_REC_ERR_ARG;
   return guarded([&] { *fastq_out = dup(ubu::Sam2Fastq().convertText(sam_in)); return UBU_REC_OK; });

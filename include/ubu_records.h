@@ -35,6 +35,11 @@ int ubu_rec_adjust_reads(const char* orig_sam, const char* to_contig_sam, const 
  * negative block lengths its arithmetic can produce). Returns 1 in *is_null where the reference returns a null read. */
 int ubu_rec_update_read_alignment(int32_t contig_pos, const uint32_t* contig_cigar, uint32_t contig_cigar_n, int32_t position, int32_t read_length,
                                   int32_t* new_start, uint32_t* cigar_out, uint32_t cigar_cap, uint32_t* cigar_n, int* is_null);
+/* CompareToReference.numDifferences (assembly/CompareToReference.java:83-123) letter for letter, IUPAC codes compared as letters ('R' vs 'A' IS a
+ * mismatch, N never is). The device form, ubu_sw_recount_batch, folds every non-ACGT letter into N: route reads for which
+ * ubu_rec_count_non_acgtn(...) > 0 (or whose reference stretch holds IUPAC codes) through this call. cigar as text ("50M2D26M"). */
+int ubu_rec_num_differences(const char* read_bases, const char* ref_bases, int32_t alignment_start, const char* cigar, int32_t* diffs);
+uint64_t ubu_rec_count_non_acgtn(const char* bases);
 int ubu_rec_sam2fastq(const char* sam_in, char** fastq_out);
 /* end1 / end2: read-name suffixes identifying the ends (Sam2Fastq.setEndSuffixes); NULL = use the FLAG bits. */
 int ubu_rec_sam2fastq_paired(const char* sam_in, const char* end1, const char* end2, char** fastq1_out, char** fastq2_out);

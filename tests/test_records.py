@@ -285,6 +285,28 @@ def test_adjust_reads_randomized(seed):
     assert want[1]["adjusted"] > 20
 
 
+def test_num_differences_compares_iupac_codes_as_letters():
+    """CompareToReference.java:90-94: 'R' vs 'A' is a mismatch, 'N' never is, case is folded. The device recount folds every non-ACGT
+    letter into N (documented divergence); the host function is letter-exact and countNonAcgtn says which reads need it."""
+    assert R.num_differences("ACGR", "ACGA", 1, "4M") == 1 and R.num_differences("ACGR", "ACGR", 1, "4M") == 0
+    assert R.num_differences("acgn", "ACGT", 1, "4M") == 0 and R.num_differences("ACGT", "ACGN", 1, "4M") == 0
+    assert R.count_non_acgtn("ACGTNacgtn") == 0 and R.count_non_acgtn("ACRYGT-") == 3
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        ref = "".join(rng.choice(list("ACGTNRYKMacgt"), size=400))
+        cig, rl, fl = [], 0, 0
+        for k in range(int(rng.integers(1, 6))):
+            op = int(rng.choice([0, 0, 1, 2, 3, 4])) if k else 0
+            n = int(rng.integers(1, 40)); cig.append((n, op))
+            rl += n if op in (0, 1, 4) else 0; fl += n if op in (0, 2) else 0
+        read = "".join(rng.choice(list("ACGTNRWacgt"), size=rl))
+        start = int(rng.integers(1, 400 - fl))
+        want = PO.num_differences(read, ref, start, cig)
+        assert R.num_differences(read, ref, start, O.cigar_text(cig)) == want
+    with pytest.raises(R.RecordsError):
+        R.num_differences("ACGT", "AC", 1, "4M")                                  # StringIndexOutOfBounds in the Java
+
+
 def test_records_library_exports_every_symbol_of_the_header():
     l = R.lib()
     hdr = open(os.path.join(ROOT, "include", "ubu_records.h")).read()

@@ -118,7 +118,7 @@ class Aligner:
                 out.write("@HD\tVN:1.4\tSO:unsorted\n")
                 for r in refs:
                     out.write(f"@SQ\tSN:{r.name}\tLN:{len(r.seq)}\n")
-                out.write("@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md)\n")
+                out.write("@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's\n")
                 if not reads:
                     return
                 wins = pack_codes([codes_from_text(r.seq) for r in refs]) if refs else None

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(HERE), "host", "libubu_host.so")
 OK, ERR_ARG, ERR_STATE, ERR_IO, ERR_ALIGNER = 0, -1, -2, -3, -4
 SYMBOLS = ["ubu_rec_combine_chimera", "ubu_rec_clean_contigs", "ubu_rec_adjust_reads", "ubu_rec_update_read_alignment", "ubu_rec_sam2fastq",
            "ubu_rec_sam2fastq_paired", "ubu_rec_align_and_clean_contigs", "ubu_rec_align_to_contigs", "ubu_rec_free", "ubu_rec_last_error",
-           "ubu_aligner_align", "ubu_aligner_short_align", "ubu_aligner_index"]
+           "ubu_aligner_align", "ubu_aligner_short_align", "ubu_aligner_index", "ubu_rec_num_differences", "ubu_rec_count_non_acgtn"]
 _lib = None
 
 
@@ -35,6 +35,7 @@ def lib() -> C.CDLL:
         l = C.CDLL(LIB_PATH)
         l.ubu_rec_last_error.restype = C.c_char_p
         l.ubu_rec_free.argtypes = [C.c_void_p]
+        l.ubu_rec_count_non_acgtn.restype = C.c_uint64
         _lib = l
     return _lib
 
@@ -110,3 +111,14 @@ def aligner_align(reference_fasta: str, input_path: str, output_sam: str, short:
     """Aligner.align / Aligner.shortAlign (Aligner.java:18-22, 46-56) through the C ABI a JNI caller binds."""
     fn = lib().ubu_aligner_short_align if short else lib().ubu_aligner_align
     _check(fn(reference_fasta.encode(), num_threads, device, input_path.encode(), output_sam.encode()))
+
+
+def num_differences(read_bases: str, ref_bases: str, alignment_start: int, cigar: str) -> int:
+    """CompareToReference.numDifferences letter for letter (IUPAC codes compared as letters)."""
+    out = C.c_int32(0)
+    _check(lib().ubu_rec_num_differences(read_bases.encode(), ref_bases.encode(), alignment_start, cigar.encode(), C.byref(out)))
+    return int(out.value)
+
+
+def count_non_acgtn(bases: str) -> int:
+    return int(lib().ubu_rec_count_non_acgtn(bases.encode()))
