@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <fstream>
 #include <sstream>
+#include <unordered_map>
 #include <stdexcept>
 #include <vector>
 
@@ -78,6 +79,33 @@ struct Packed {
   }
 };
 
+// exact k-mer index over the reference sequences (k <= 31, 2 bits per base, k-mers with a non-ACGT letter skipped)
+struct SeedIndex {
+  int k = 0; std::unordered_map<uint64_t, std::vector<uint32_t>> map;
+  static int code(char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'T': case 't': return 2; case 'G': case 'g': return 3; default: return -1; } }
+  template <class F> void each_kmer(const std::string& s, F f) const {
+    const uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    uint64_t v = 0; int run = 0;
+    for (char ch : s) {
+      const int c = code(ch);
+      if (c < 0) { run = 0; v = 0; continue; }
+      v = ((v << 2) | (uint64_t)c) & mask;
+      if (++run >= k) f(v);
+    }
+  }
+  void build(const std::vector<Rec>& refs, int kk) {
+    k = kk;
+    for (size_t w = 0; w < refs.size(); ++w)
+      each_kmer(refs[w].seq, [&](uint64_t v) { std::vector<uint32_t>& l = map[v]; if (l.empty() || l.back() != (uint32_t)w) l.push_back((uint32_t)w); });
+  }
+  std::vector<uint32_t> candidates(const std::string& read) const {          // ascending window order
+    std::vector<uint32_t> out;
+    each_kmer(read, [&](uint64_t v) { auto it = map.find(v); if (it != map.end()) out.insert(out.end(), it->second.begin(), it->second.end()); });
+    std::sort(out.begin(), out.end()); out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+  }
+};
+
 std::string cigar_text(const uint32_t* ops, uint32_t n) {
   char buf[4096];
   ubu_sw_cigar_string(ops, n, buf, sizeof buf);
@@ -103,16 +131,20 @@ void Aligner::run(const std::string& input, const std::string& outputSam) {
   const std::vector<Rec> reads = read_fastx(input);
   std::ofstream out(outputSam);
   if (!out) throw std::runtime_error("cannot write " + outputSam);
+  int seed_k = seedK_;
+  if (seed_k < 0) { const char* e = getenv("UBU_ALIGNER_SEED_K"); seed_k = e ? atoi(e) : 0; }
+  seed_k = std::max(0, std::min(seed_k, 31));
   out << "@HD\tVN:1.4\tSO:unsorted\n";
   for (const Rec& r : refs) out << "@SQ\tSN:" << r.name << "\tLN:" << r.seq.size() << "\n";
-  out << "@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's\n";
+  out << "@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's"
+      << (seed_k > 0 ? "; candidates = sequences sharing an exact " + std::to_string(seed_k) + "-mer with the read" : std::string()) << "\n";
   auto unmapped = [&](const Rec& rd) {
     out << rd.name << "\t4\t*\t0\t0\t*\t*\t0\t0\t" << rd.seq << "\t" << (rd.has_qual && !rd.qual.empty() ? rd.qual : "*") << "\n";
   };
   if (reads.empty()) return;
   if (refs.empty()) { for (const Rec& rd : reads) unmapped(rd); return; }
   for (const Rec& r : refs) if (r.seq.size() > UBU_SW_MAX_WINDOW) throw std::runtime_error("reference sequence longer than 65535: " + r.name);
-  for (const Rec& r : reads) if (r.seq.size() > UBU_SW_MAX_READ) throw std::runtime_error("read longer than 256: " + r.name);
+  for (const Rec& r : reads) if (r.seq.size() > UBU_SW_MAX_READ) throw std::runtime_error("read longer than 4096: " + r.name);
 
   if (!handle_) {
     ubu_sw_params p{match_, mismatch_, gapOpen_, gapExt_};
@@ -126,15 +158,26 @@ void Aligner::run(const std::string& input, const std::string& outputSam) {
   Packed W;
   for (const Rec& r : refs) W.add(r.seq);
   const size_t nw = refs.size();
-  const size_t per_batch = std::max<size_t>(1, 2000000 / std::max<size_t>(1, 2 * nw));
+  SeedIndex seeds;
+  if (seed_k > 0) seeds.build(refs, seed_k);
+  const size_t per_batch = seed_k > 0 ? 500000 : std::max<size_t>(1, 2000000 / std::max<size_t>(1, 2 * nw));
   for (size_t lo = 0; lo < reads.size(); lo += per_batch) {
     const size_t hi = std::min(reads.size(), lo + per_batch), nr = hi - lo;
     Packed R;                                    // entries: fwd_0, rc_0, fwd_1, rc_1, ...
     for (size_t k = lo; k < hi; ++k) { R.add(reads[k].seq); R.add(revcomp(reads[k].seq)); }
-    const size_t nt = 2 * nr * nw;               // task (entry e, window w) = e * nw + w, sharing the packed bytes
-    std::vector<uint32_t> toff(nt), tnoff(nt), widx(nt); std::vector<uint16_t> tlen(nt);
-    for (size_t e = 0; e < 2 * nr; ++e)
-      for (size_t w = 0; w < nw; ++w) { const size_t t = e * nw + w; toff[t] = R.off[e]; tnoff[t] = R.noff[e]; tlen[t] = R.len[e]; widx[t] = (uint32_t)w; }
+    // tasks: (entry e, window w) pairs sharing the packed bytes -- all of them, or the seeded candidates; entry_first[e] .. entry_first[e+1]
+    // are entry e's tasks in window order
+    std::vector<uint32_t> toff, tnoff, widx, entry_first(2 * nr + 1, 0); std::vector<uint16_t> tlen;
+    for (size_t e = 0; e < 2 * nr; ++e) {
+      entry_first[e] = (uint32_t)widx.size();
+      std::vector<uint32_t> cand;
+      if (seed_k > 0) cand = seeds.candidates(e % 2 ? revcomp(reads[lo + e / 2].seq) : reads[lo + e / 2].seq);
+      else { cand.resize(nw); for (size_t w = 0; w < nw; ++w) cand[w] = (uint32_t)w; }
+      for (uint32_t w : cand) { toff.push_back(R.off[e]); tnoff.push_back(R.noff[e]); tlen.push_back(R.len[e]); widx.push_back(w); }
+    }
+    entry_first[2 * nr] = (uint32_t)widx.size();
+    const size_t nt = widx.size();
+    if (nt == 0) { for (size_t k = lo; k < hi; ++k) unmapped(reads[k]); continue; }
     ubu_sw_seqs rs{}, ws{};
     rs.packed = R.packed.data(); rs.off = toff.data(); rs.len = tlen.data(); rs.count = (uint32_t)nt; rs.packed_bytes = (uint32_t)R.packed.size();
     if (R.any_n) { rs.nmask = R.nmask.data(); rs.nmask_off = tnoff.data(); rs.nmask_bytes = (uint32_t)R.nmask.size(); }
@@ -149,15 +192,26 @@ void Aligner::run(const std::string& input, const std::string& outputSam) {
 
     for (size_t k = 0; k < nr; ++k) {
       const Rec& rd = reads[lo + k];
-      auto task = [&](size_t w, int s) { return (2 * k + (size_t)s) * nw + w; };
+      // this read's tasks as (window, strand, task), reference order, plus strand first
+      struct Cand { uint32_t w; int s; size_t t; };
+      std::vector<Cand> cands;
+      {
+        size_t a = entry_first[2 * k], a1 = entry_first[2 * k + 1], b = a1, b1 = entry_first[2 * k + 2];
+        while (a < a1 || b < b1) {
+          if (b >= b1 || (a < a1 && widx[a] <= widx[b])) { cands.push_back({widx[a], 0, a}); ++a; } else { cands.push_back({widx[b], 1, b}); ++b; }
+        }
+      }
+      std::unordered_map<uint64_t, size_t> task_of;
+      for (const Cand& c : cands) task_of[((uint64_t)c.w << 1) | (uint64_t)c.s] = c.t;
+      auto task = [&](size_t w, int s) { return task_of[((uint64_t)w << 1) | (uint64_t)s]; };
       int best = 0;
-      for (size_t w = 0; w < nw; ++w) for (int s = 0; s < 2; ++s) best = std::max(best, res[task(w, s)].score);
+      for (const Cand& c : cands) best = std::max(best, res[c.t].score);
       if (best <= 0) { unmapped(rd); continue; }
       std::vector<std::pair<size_t, int>> hits;                   // reference order, plus strand first
       int x1 = 0;
-      for (size_t w = 0; w < nw; ++w) for (int s = 0; s < 2; ++s) {
-        const int sc = res[task(w, s)].score;
-        if (sc == best) hits.push_back({w, s});
+      for (const Cand& c : cands) {
+        const int sc = res[c.t].score;
+        if (sc == best) hits.push_back({c.w, c.s});
         else if (sc >= best - (match_ - mismatch_) && sc < best) ++x1;
       }
       const size_t t0 = task(hits[0].first, hits[0].second);

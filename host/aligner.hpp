@@ -25,11 +25,16 @@ class Aligner {
   void align(const std::string& input, const std::string& outputSam);
   void shortAlign(const std::string& input, const std::string& outputSam);
   void index();
+  // BUILD-DEFINED scalability switch (the reference hands candidate finding to bwa's index): k > 0 aligns a read (either strand) only
+  // against the reference sequences it shares at least one exact k-mer with (k <= 31); a hit without any exact k-mer match is then not
+  // reported. 0 (default) = every read x every sequence x both strands. Also read from the environment variable UBU_ALIGNER_SEED_K.
+  void setSeedLength(int k) { seedK_ = k; }
 
  private:
   void run(const std::string& input, const std::string& outputSam);
   std::string reference_;
   int numThreads_, device_, match_, mismatch_, gapOpen_, gapExt_;
+  int seedK_ = -1;              // -1: take UBU_ALIGNER_SEED_K (or 0)
   void* handle_ = nullptr;      // ubu_sw_handle*, created on first use
 };
 

@@ -89,6 +89,43 @@ def test_failure_surfaces_as_runtime_error(tmp_path):
         a.shortAlign(str(tmp_path / "nope.fq"), str(tmp_path / "o.sam"))
 
 
+def test_seed_filter_aligns_only_candidate_pairs(tmp_path):
+    """seed_k > 0 (BUILD-DEFINED scalability switch): a read meets only the sequences it shares an exact k-mer with. Reads with such a
+    seed get the record all-vs-all gives them (X0/X1 may only shrink); the number of alignment tasks drops from reads x contigs x 2."""
+    rng = np.random.default_rng(21)
+    contigs = [(f"ctg{k}", "".join(rng.choice(list("ACGT"), size=300))) for k in range(12)]
+    reads = []
+    for k in range(60):
+        c = contigs[int(rng.integers(0, 12))][1]
+        s0 = int(rng.integers(0, 220))
+        r = list(c[s0:s0 + 76]); r[10] = "A" if r[10] != "A" else "C"; r[50] = "G" if r[50] != "G" else "T"
+        r = "".join(r)
+        reads.append((f"r{k}", U.reverse_complement(r) if k % 2 else r))
+    reads.append(("noseed", "ACGTTGCA" * 6))
+    ref, fq = write_inputs(tmp_path, reads, contigs)
+    counts = []
+
+    def counting(rs, ws, ix):
+        counts.append(rs.count)
+        return oracle_align_fn(rs, ws, ix)
+
+    out = {}
+    for k in (0, 16):
+        counts.clear()
+        a = Aligner(ref, 1, align_fn=counting, seed_k=k)
+        a.shortAlign(fq, str(tmp_path / f"o{k}.sam")); a.close()
+        out[k] = (parse_sam(str(tmp_path / f"o{k}.sam")), sum(counts), open(tmp_path / f"o{k}.sam").read())
+    assert out[0][1] == len(reads) * len(contigs) * 2 and out[16][1] <= 2 * len(reads)           # ~1 task per read instead of 24
+    assert "candidates = sequences sharing an exact 16-mer" in out[16][2] and "candidates" not in out[0][2]
+    for full, seeded in zip(out[0][0], out[16][0]):
+        if full["qname"] == "noseed":
+            assert seeded["flag"] == 4                                                           # no exact 16-mer anywhere: not attempted
+            continue
+        for f in ("flag", "rname", "pos", "cigar", "seq"):
+            assert full[f] == seeded[f], (full["qname"], f)
+        assert full["tags"]["NM"] == seeded["tags"]["NM"] and int(seeded["tags"]["X0"]) <= int(full["tags"]["X0"])
+
+
 @pytest.mark.gpu
 def test_device_writes_the_same_sam_as_the_oracle_stand_in(tmp_path):
     rng = np.random.default_rng(4)
@@ -157,3 +194,8 @@ def test_cpp_host_writes_the_same_sam_as_the_python_facade(tmp_path):
     r = subprocess.run([CLI, "shortAlign", ref, fq, str(tmp_path / "cpp.sam")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(tmp_path / "py.sam").read() == open(tmp_path / "cpp.sam").read()
+    # the same with the seed filter on both sides (ubu::Aligner::setSeedLength / UBU_ALIGNER_SEED_K == facade.Aligner(seed_k=...))
+    a = Aligner(ref, 1, seed_k=14); a.shortAlign(fq, str(tmp_path / "py14.sam")); a.close()
+    r = subprocess.run([CLI, "shortAlign", ref, fq, str(tmp_path / "cpp14.sam")], capture_output=True, text=True, env=dict(os.environ, UBU_ALIGNER_SEED_K="14"))
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "py14.sam").read() == open(tmp_path / "cpp14.sam").read()

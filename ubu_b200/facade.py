@@ -77,11 +77,15 @@ class Aligner:
 
     def __init__(self, reference: str, numThreads: int = 1, device: int = 0, match: int = 1, mismatch: int = -3,
                  gap_open: int = 5, gap_ext: int = 2, align_fn: Optional[Callable[[SeqSet, SeqSet, np.ndarray], Alignments]] = None,
-                 batch_tasks: int = 2_000_000):
+                 batch_tasks: int = 2_000_000, seed_k: int = 0):
         self.reference, self.numThreads = reference, numThreads        # Aligner.java:9-16 (numThreads unused: one GPU per handle)
         self.scoring = (match, mismatch, gap_open, gap_ext)
         self._device, self._align_fn, self._sw = device, align_fn, None
+        self._seeds = None
         self._batch = batch_tasks
+        # BUILD-DEFINED scalability switch (mirrors ubu::Aligner::setSeedLength): k > 0 aligns a read (either strand) only against the
+        # reference sequences it shares an exact k-mer with; 0 = every read x every sequence x both strands
+        self.seed_k = max(0, min(int(seed_k), 31))
 
     # -- reference API ---------------------------------------------------------------------------
     def index(self) -> None:
@@ -118,11 +122,13 @@ class Aligner:
                 out.write("@HD\tVN:1.4\tSO:unsorted\n")
                 for r in refs:
                     out.write(f"@SQ\tSN:{r.name}\tLN:{len(r.seq)}\n")
-                out.write("@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's\n")
+                out.write("@PG\tID:ubu_b200\tPN:ubu_b200\tDS:window Smith-Waterman on B200 (SPEC.md); X0 X1 XA MAPQ rules are BUILD-DEFINED (best = highest score, X1 = within one mismatch of it, MAPQ 37/23/0), not bwa's"
+                          + (f"; candidates = sequences sharing an exact {self.seed_k}-mer with the read" if self.seed_k > 0 else "") + "\n")
                 if not reads:
                     return
                 wins = pack_codes([codes_from_text(r.seq) for r in refs]) if refs else None
-                per_batch = max(1, self._batch // max(1, 2 * len(refs)))
+                per_batch = max(1, self._batch // max(1, 2 * len(refs))) if self.seed_k == 0 else 500_000
+                self._seeds = self._seed_index(refs) if self.seed_k > 0 else None
                 for lo in range(0, len(reads), per_batch):
                     self._align_and_write(reads[lo:lo + per_batch], refs, wins, out)
         except (OSError, ValueError) as e:                               # the reference surfaces every failure as RuntimeException
@@ -140,24 +146,34 @@ class Aligner:
             texts.append(rd.seq)
             texts.append(reverse_complement(rd.seq))
         base = pack_codes([codes_from_text(t) for t in texts])
-        ent = np.repeat(np.arange(2 * nr), nw)                           # task -> read entry
-        widx = np.tile(np.arange(nw, dtype=np.uint32), 2 * nr)           # task -> window
+        # tasks: (entry, window) pairs -- all of them, or the seeded candidates (ascending window order per entry)
+        cand = [list(range(nw)) if self._seeds is None else self._candidates(t) for t in texts]
+        ent = np.repeat(np.arange(2 * nr), [len(c) for c in cand])       # task -> read entry
+        widx = np.array([w for c in cand for w in c], dtype=np.uint32)   # task -> window
+        if widx.size == 0:
+            for rd in reads:
+                out.write(self._unmapped(rd))
+            return
+        first = np.concatenate([[0], np.cumsum([len(c) for c in cand])])
         tasks = SeqSet(base.packed, base.off[ent], base.len[ent], base.nmask, None if base.nmask is None else base.nmask_off[ent])
         al = self._device_align(tasks, wins, widx)
-        score = al.results["score"].reshape(nr, 2, nw).astype(np.int64)
+        score = al.results["score"].astype(np.int64)
         m, x = self.scoring[0], self.scoring[1]
         for k, rd in enumerate(reads):
-            sc = score[k]                                                # [strand, window]
-            best = int(sc.max())
+            # this read's tasks as (window, strand) -> task, reference order, plus strand first
+            task_of = {}
+            for s in (0, 1):
+                for j, w in enumerate(cand[2 * k + s]):
+                    task_of[(w, s)] = int(first[2 * k + s]) + j
+            order = sorted(task_of)
+            best = max((int(score[task_of[ws]]) for ws in order), default=0)
             if best <= 0:
                 out.write(self._unmapped(rd))
                 continue
-            # hit order: reference order, plus strand first
-            order = [(w, s) for w in range(nw) for s in (0, 1)]
-            best_hits = [(w, s) for (w, s) in order if sc[s, w] == best]
-            x1 = sum(1 for (w, s) in order if best - (m - x) <= sc[s, w] < best)
+            best_hits = [ws for ws in order if score[task_of[ws]] == best]
+            x1 = sum(1 for ws in order if best - (m - x) <= score[task_of[ws]] < best)
             w0, s0 = best_hits[0]
-            t0 = (2 * k + s0) * nw + w0
+            t0 = task_of[(w0, s0)]
             r0 = al.results[t0]
             cig = cigar_text(al.cigar(t0))
             nm = int(r0["edit_distance"])
@@ -171,12 +187,35 @@ class Aligner:
             if len(best_hits) > 1:
                 xa = []
                 for (w, s) in best_hits[1:MAX_XA + 1]:
-                    t = (2 * k + s) * nw + w
+                    t = task_of[(w, s)]
                     rr = al.results[t]
                     xa.append(f"{refs[w].name},{'-' if s else '+'}{int(rr['ref_start'])},{cigar_text(al.cigar(t))},{int(rr['edit_distance'])};")
                 tags.append("XA:Z:" + "".join(xa))
             flag = 16 if s0 else 0
             out.write("\t".join([rd.name, str(flag), refs[w0].name, str(int(r0["ref_start"])), str(mapq), cig, "*", "0", "0", seq, qual] + tags) + "\n")
+
+    # -- exact k-mer seeds (k-mers holding a non-ACGT letter are skipped) ---------------------------
+    def _kmers(self, text: str):
+        k, t = self.seed_k, text.upper()
+        for i in range(len(t) - k + 1):
+            km = t[i:i + k]
+            if all(c in "ACGT" for c in km):
+                yield km
+
+    def _seed_index(self, refs: List[FastxRecord]) -> dict:
+        idx: dict = {}
+        for w, r in enumerate(refs):
+            for km in self._kmers(r.seq):
+                lst = idx.setdefault(km, [])
+                if not lst or lst[-1] != w:
+                    lst.append(w)
+        return idx
+
+    def _candidates(self, text: str) -> List[int]:
+        out = set()
+        for km in self._kmers(text):
+            out.update(self._seeds.get(km, ()))
+        return sorted(out)
 
     @staticmethod
     def _unmapped(rd: FastxRecord) -> str:
