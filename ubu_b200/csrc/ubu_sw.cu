@@ -1077,6 +1077,11 @@ int ubu_sw_align_batch(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_
     const int rc = align_stream(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, cigar_pool_used);
     if (rc != kNoStream) return rc;
   }
+  if (h) {                                // sequential synchronous calls reuse slot 0 (and its scratch) instead of rotating through the slots
+    bool any_pending = false;
+    for (int k = 0; k < h->n_slots; ++k) any_pending = any_pending || h->slots[k].pending;
+    if (!any_pending) h->next_slot = 0;
+  }
   int ticket = -1;
   int rc = ubu_sw_submit(h, reads, windows, pair_ref_idx, out, cigar_pool, cigar_pool_cap, &ticket);
   if (rc) return rc;
