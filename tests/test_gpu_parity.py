@@ -630,3 +630,48 @@ def test_extreme_scoring_with_long_reads():
         al = a.align(r, ws)
     check_against_oracle(al, r, ws, None, params)
     assert int(al.results[0]["score"]) == 31 * 2000
+
+
+def test_cfg5_shape_through_the_multi_gpu_driver():
+    """BASELINE.json configs[4] in shape (150 bp reads vs 2 kb windows, reads grouped by window, generated shard by shard from
+    (seed, shard)) at 2 % of its size, through ubu_sw_multi_align on every visible GPU: size-independent properties over all
+    2 M records, an oracle-checked sample, SAM line count, and equality with one ubu_sw_align_batch call on one GPU."""
+    import os
+
+    from ubu_b200 import multi as M
+
+    n = 2_000_000
+    w = WL.cfg3_sharded(n, shard=250_000, seed=WL.SEEDS["cfg5"], threads=8)
+    with M.MultiAligner(slots=4) as m:
+        fd = os.open(os.devnull, os.O_WRONLY)
+        try:
+            al = m.align(w.reads, w.windows, w.pair_ref_idx, sam_fd=fd)
+        finally:
+            os.close(fd)
+        sam_bytes = m.last_sam_bytes
+    r = al.results
+    assert len(al) == n and int((r["flags"] & 1).sum()) == 0 and int(r["score"].min()) > 40 and int(r["score"].max()) <= 150
+    assert np.all(r["ref_end"] <= 2000) and np.all(r["ref_start"] >= 1) and np.all(r["q_end"] >= r["q_start"])
+    # every CIGAR slice lies inside the pool, slices do not overlap, and every CIGAR covers its read
+    order = np.argsort(r["cigar_off"], kind="stable")
+    starts, cn = r["cigar_off"][order].astype(np.int64), r["cigar_n"][order].astype(np.int64)
+    assert np.all(starts[1:] >= starts[:-1] + cn[:-1]) and starts[-1] + cn[-1] <= al.cigar_pool.shape[0]
+    task = np.repeat(np.arange(n), r["cigar_n"].astype(np.int64))
+    k = np.arange(task.shape[0]) - np.repeat(np.concatenate([[0], np.cumsum(r["cigar_n"].astype(np.int64))[:-1]]), r["cigar_n"].astype(np.int64))
+    ops = al.cigar_pool[r["cigar_off"].astype(np.int64)[task] + k]
+    lens, kinds = (ops >> 4).astype(np.int64), ops & 15
+    assert np.all(np.bincount(task, weights=np.where(np.isin(kinds, (0, 1, 4)), lens, 0), minlength=n) == 150)
+    assert np.all(np.bincount(task, weights=np.where(np.isin(kinds, (0, 2)), lens, 0), minlength=n) == r["ref_end"].astype(np.int64) - r["ref_start"] + 1)
+    assert sam_bytes > n * 200                                     # one SAM line per read was formatted
+    # oracle on a sample
+    pick = np.sort(np.random.default_rng(2).choice(n, size=3000, replace=False))
+    q = [w.reads.codes(int(t)) for t in pick]
+    wi = [w.windows.codes(int(w.pair_ref_idx[t])) for t in pick]
+    ores, ocig = O.align_batch(q, wi, None, nthreads=8)
+    for j, t in enumerate(pick):
+        assert all(int(r[int(t)][f]) == int(ores[j][f]) for f in FIELDS) and al.cigar(int(t)) == ocig[j]
+    # one call on one GPU gives the same records
+    with U.SwAligner(slots=4) as a:
+        one = a.align(w.reads, w.windows, w.pair_ref_idx)
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(one.results[f], r[f]), f
