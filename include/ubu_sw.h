@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define UBU_SW_VERSION 0x00010000u
+#define UBU_SW_VERSION 0x00020000u   /* round 2: multi-GPU driver, long reads, ubu_sw_sam_names.cigar_pool_n */
 
 typedef enum {
   UBU_SW_OK = 0,

@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
 
 def test_version_and_errors():
     lib = N.lib()
-    assert lib.ubu_sw_version() == 0x00010000
+    assert lib.ubu_sw_version() == 0x00020000
     assert lib.ubu_sw_strerror(0) == b"ok"
     assert b"CIGAR" in lib.ubu_sw_strerror(N.ERR_CIGAR_POOL)
     assert lib.ubu_sw_strerror(-99) == b"unknown status"
