@@ -63,7 +63,7 @@ sw_long_kernel(TbArgs a, LongArgs la) {
     for (int j = lane; j < W + 33; j += 32) { Hb[j] = 0; Fb[j] = TB_NEG; }
     __syncwarp();
 
-    unsigned long long best = 0ull;                            // (score << 32) | (0xFFFF - j) << 16 | (0xFFFF - i)
+    int best_h = 0, best_j = 0, best_i = 0;                    // this lane's best cell: highest score, then smallest column, then smallest row
     for (int s0 = 0; s0 < L; s0 += 32) {
       const int i = s0 + lane + 1;                             // 1-based row of this lane
       const bool active = i <= L;
@@ -104,8 +104,7 @@ sw_long_kernel(TbArgs a, LongArgs la) {
         diag = up_h;
         if (valid) {
           h_left = h; e = ev;
-          const unsigned long long key = ((unsigned long long)(uint32_t)h << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)j) << 16) | (unsigned long long)(0xFFFFu - (uint32_t)i);
-          if (h > 0 && key > best) best = key;
+          if (h > best_h || (h == best_h && h > 0 && j < best_j)) { best_h = h; best_j = j; best_i = i; }   // (a later stripe's equal cell has a larger row: kept out)
           word |= nib << (4 * ((j - 1) & 7));
           if (((j - 1) & 7) == 7 || j == W) { drow[(j - 1) >> 3] = word; word = 0u; }
           if (lane == 31) { Hb[j] = h; Fb[j] = f; }            // boundary for the next stripe (lane 0 is 31 columns ahead: in place)
@@ -116,6 +115,9 @@ sw_long_kernel(TbArgs a, LongArgs la) {
       }
       __syncwarp();
     }
+    // SPEC section 4 across the lanes: (score, -j, -i) as one key
+    unsigned long long best = best_h > 0 ? (((unsigned long long)(uint32_t)best_h << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)best_j) << 16) |
+                                            (unsigned long long)(0xFFFFu - (uint32_t)best_i)) : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
     __syncwarp();

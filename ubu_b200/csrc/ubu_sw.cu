@@ -603,8 +603,9 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
     }
     per = (per + 255) & ~(size_t)255;
     const size_t warps_per_cta = LONG_THREADS / 32;
-    size_t ctas = std::min<size_t>((s.long_tasks.size() + warps_per_cta - 1) / warps_per_cta, (size_t)h->sm_count * 2);
-    ctas = std::max<size_t>(1, std::min<size_t>(ctas, ((size_t)4 << 30) / (per * warps_per_cta)));
+    // the kernel is latency-bound (a dependent chain per 32-cell step): it wants ~16 warps per SM, which only the scratch limits
+    size_t ctas = std::min<size_t>((s.long_tasks.size() + warps_per_cta - 1) / warps_per_cta, (size_t)h->sm_count * 4);
+    ctas = std::max<size_t>(1, std::min<size_t>(ctas, ((size_t)12 << 30) / (per * warps_per_cta)));
     s.long_per_warp = per; s.long_grid = (int)ctas;
     CU(h, s.d_long.reserve(ctas * warps_per_cta * per + 256));
   }
