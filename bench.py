@@ -115,6 +115,15 @@ def measured_int_peak() -> dict:
             "sm_mhz": data["observed_sm_mhz"], "alu_only_roofline_gcups": data.get("alu_only_roofline_gcups")}
 
 
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s: MEASURED_PEAKS.json (driver-written) when present, else the recipe's figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6551.4, "fallback: the figure MEASURED_PEAKS.json held when this round was built"
+
+
 def ncu_traffic(kernel_key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel on the headline workload, from this
     round's `ncu --set full` capture (profiles/traffic_<round>.json, written by tools/ncu_summary.py from the .ncu-rep)."""
@@ -635,8 +644,8 @@ def main():
             "ops_per_cell": 7, "launch_ms": fwd_s * 1e3, "share_of_step": float(np.mean(fwd_ms) / np.mean(ev_ms)),
             "traffic": traffic, "traffic_unit": "bytes per step's forward launches (dram__bytes_read.sum + dram__bytes_write.sum)",
             "traffic_source": traffic_src,
-            "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": 6551.4,
-                    "frac": algo_bytes / fwd_s / 1e9 / 6551.4, "note": "not the bound: ~5e-4 B/cell"},
+            "hbm": {"algorithmic_bytes_per_launch": int(algo_bytes), "achieved_gbs": algo_bytes / fwd_s / 1e9, "peak_gbs": hbm_peak_gbs()[0],
+                    "peak_source": hbm_peak_gbs()[1], "frac": algo_bytes / fwd_s / 1e9 / hbm_peak_gbs()[0], "note": "not the bound: ~5e-4 B/cell"},
         }
         line = {
             "metric": "SW realignment GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
