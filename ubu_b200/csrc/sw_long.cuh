@@ -3,9 +3,9 @@
 //
 // These are few (one per assembled contig, not one per read) and long, so the kernel is built for generality, not for the
 // roofline: 32-bit arithmetic (no score can overflow: match <= 31, L <= 4096), one WARP per task, the whole matrix.
-// Lane l owns row s0 + l of the current 32-row stripe and sweeps the window as a skewed wavefront (lane l is at column
-// step - l + 1); what a lane needs from the row above (H, F) and the window base of its column arrive by warp shuffle from
-// lane l-1, which was at that column one step earlier. Lane 0 takes them from the stripe above (a per-warp boundary row in global
+// Lane l owns LONG_K consecutive rows of the current stripe of 32 x LONG_K rows and sweeps the window as a skewed wavefront
+// (lane l is at column step - l + 1); what a lane needs from the row above its rows (H, F) and the window base of its column
+// arrive by warp shuffle from lane l-1, which was at that column one step earlier. Lane 0 takes them from the stripe above (a per-warp boundary row in global
 // memory, written in place by lane 31; read 32 columns per coalesced load and handed to lane 0 by shuffle) and from the packed
 // window (same scheme). Every cell stores a direction nibble (8 cells per 32-bit word per lane) into a per-warp L x W
 // matrix: bits 0-1 = where H came from (0 stop, 1 diagonal, 2 F, 3 E), bit 2 = F was extended, bit 3 = E was extended --
@@ -18,6 +18,10 @@
 namespace ubu {
 
 constexpr int LONG_THREADS = 128;
+#ifndef UBU_LONG_K
+#define UBU_LONG_K 8
+#endif
+constexpr int LONG_K = UBU_LONG_K;                                // rows per lane: a stripe is 32 x LONG_K rows
 constexpr uint32_t LONG_MAX_READ = 4096;                 // = UBU_SW_MAX_READ
 constexpr uint64_t LONG_MAX_CELLS = (uint64_t)1 << 26;   // L x W of one task: 32 MB of direction nibbles per warp at most
 
@@ -64,15 +68,23 @@ sw_long_kernel(TbArgs a, LongArgs la) {
     __syncwarp();
 
     int best_h = 0, best_j = 0, best_i = 0;                    // this lane's best cell: highest score, then smallest column, then smallest row
-    for (int s0 = 0; s0 < L; s0 += 32) {
-      const int i = s0 + lane + 1;                             // 1-based row of this lane
-      const bool active = i <= L;
-      const uint32_t qc = active ? base2(t.q, (uint32_t)(i - 1)) : 0u;
-      const bool qn = HAS_N && active && t.qn && nbit(t.qn, (uint32_t)(i - 1));
-      int h_left = 0, e = TB_NEG, diag = 0;                    // H[i][j-1], E[i][j-1], H[i-1][j-1]
-      int out_h = 0, out_f = TB_NEG; uint32_t out_c = 0u;      // what this lane hands to the lane below: H[i][j], F[i][j], window base (+4 = N)
-      uint32_t word = 0u;
-      uint32_t* drow = dir + (size_t)(active ? i - 1 : 0) * wpr;
+    for (int s0 = 0; s0 < L; s0 += 32 * LONG_K) {
+      const int i0 = s0 + lane * LONG_K + 1;                   // 1-based first row of this lane
+      const int nact = max(0, min(LONG_K, L - (i0 - 1)));      // rows of this lane inside the read
+      uint32_t qcodes = 0u, qnbits = 0u;                       // 2-bit codes / N flags of the lane's rows
+#pragma unroll
+      for (int k = 0; k < LONG_K; ++k) {
+        if (k < nact) {
+          qcodes |= base2(t.q, (uint32_t)(i0 - 1 + k)) << (2 * k);
+          if (HAS_N && t.qn && nbit(t.qn, (uint32_t)(i0 - 1 + k))) qnbits |= 1u << k;
+        }
+      }
+      int hl[LONG_K], ee[LONG_K]; uint32_t wd[LONG_K];         // H[i][j-1], E[i][j-1], direction nibbles being collected, per row
+#pragma unroll
+      for (int k = 0; k < LONG_K; ++k) { hl[k] = 0; ee[k] = TB_NEG; wd[k] = 0u; }
+      int dgtop = 0;                                           // H[i0-1][j-1]
+      int out_h = 0, out_f = TB_NEG; uint32_t out_c = 0u;      // what this lane hands to the lane below: H, F of its bottom row, window base (+4 = N)
+      uint32_t* drow = dir + (size_t)(i0 - 1) * wpr;
       // blocks of 32 columns for lane 0: boundary values and window bases, one coalesced load per block, one block ahead
       int hb_n = Hb[1 + lane], fb_n = Fb[1 + lane];
       uint32_t rc_n = (lane < W) ? (base2(t.r, (uint32_t)lane) | ((HAS_N && t.rn && nbit(t.rn, (uint32_t)lane)) ? 4u : 0u)) : 0u;
@@ -85,33 +97,42 @@ sw_long_kernel(TbArgs a, LongArgs la) {
           hb_n = Hb[min(jn + 1, W + 32)]; fb_n = Fb[min(jn + 1, W + 32)];
           rc_n = (jn < W) ? (base2(t.r, (uint32_t)jn) | ((HAS_N && t.rn && nbit(t.rn, (uint32_t)jn)) ? 4u : 0u)) : 0u;
         }
-        // from the row above: lane l-1's output of the previous step is column j of row i-1
-        int up_h = __shfl_up_sync(0xffffffffu, out_h, 1), up_f = __shfl_up_sync(0xffffffffu, out_f, 1);
+        // from the rows above: lane l-1's bottom-row output of the previous step is column j of row i0-1
+        int uh = __shfl_up_sync(0xffffffffu, out_h, 1), uf = __shfl_up_sync(0xffffffffu, out_f, 1);
         uint32_t rc = __shfl_up_sync(0xffffffffu, out_c, 1);
         const int b_h = __shfl_sync(0xffffffffu, hb, step & 31), b_f = __shfl_sync(0xffffffffu, fb, step & 31);
         const uint32_t b_c = __shfl_sync(0xffffffffu, rcb, step & 31);
-        if (lane == 0) { up_h = b_h; up_f = b_f; rc = b_c; }
+        if (lane == 0) { uh = b_h; uf = b_f; rc = b_c; }
         const int j = step - lane + 1;                         // 1-based column of this lane
-        const bool valid = active && j >= 1 && j <= W;
-        const int fe = up_f - ext, fo = up_h - oe, f = max(fe, fo);
-        const int ee = e - ext, eo = h_left - oe, ev = max(ee, eo);
-        int s = ((rc & 3u) == qc) ? ma : mm;
-        if (HAS_N && (qn || (rc & 4u))) s = 0;
-        const int d = diag + s;
-        int h = max(max(d, ev), max(f, 0));
-        uint32_t nib = (h == 0) ? 0u : (h == d) ? 1u : (h == f) ? 2u : 3u;
-        nib |= (fe >= fo ? 4u : 0u) | (ee >= eo ? 8u : 0u);
-        diag = up_h;
-        if (valid) {
-          h_left = h; e = ev;
-          if (h > best_h || (h == best_h && h > 0 && j < best_j)) { best_h = h; best_j = j; best_i = i; }   // (a later stripe's equal cell has a larger row: kept out)
-          word |= nib << (4 * ((j - 1) & 7));
-          if (((j - 1) & 7) == 7 || j == W) { drow[(j - 1) >> 3] = word; word = 0u; }
-          if (lane == 31) { Hb[j] = h; Fb[j] = f; }            // boundary for the next stripe (lane 0 is 31 columns ahead: in place)
-        } else {
-          h = 0; h_left = 0; e = TB_NEG;                       // column 0 / outside: the matrix boundary
+        const bool colvalid = j >= 1 && j <= W;
+        const uint32_t sh = 4u * (uint32_t)((j - 1) & 7);
+        int dg = dgtop;                                        // H[i-1][j-1] of the row being updated
+        dgtop = uh;
+#pragma unroll
+        for (int k = 0; k < LONG_K; ++k) {
+          const int fe = uf - ext, fo = uh - oe, f = max(fe, fo);
+          const int e2 = ee[k] - ext, eo = hl[k] - oe, ev = max(e2, eo);
+          int s = ((rc & 3u) == ((qcodes >> (2 * k)) & 3u)) ? ma : mm;
+          if (HAS_N && (((qnbits >> k) & 1u) || (rc & 4u))) s = 0;
+          const int d = dg + s;
+          const int h = max(max(d, ev), max(f, 0));
+          uint32_t nib = (h == 0) ? 0u : (h == d) ? 1u : (h == f) ? 2u : 3u;
+          nib |= (fe >= fo ? 4u : 0u) | (e2 >= eo ? 8u : 0u);
+          dg = hl[k];                                          // the old left value is the diagonal of the row below
+          const bool v = colvalid && k < nact;
+          if (v) {
+            hl[k] = h; ee[k] = ev;
+            if (h > best_h || (h == best_h && h > 0 && j < best_j)) { best_h = h; best_j = j; best_i = i0 + k; }   // rows ascend: the smaller row keeps a tie
+            wd[k] |= nib << sh;
+          } else if (!colvalid) { hl[k] = 0; ee[k] = TB_NEG; }   // column 0 / outside: the matrix boundary
+          uh = v ? h : 0; uf = v ? f : TB_NEG;
         }
-        out_h = h; out_f = valid ? f : TB_NEG; out_c = rc;
+        out_h = uh; out_f = uf; out_c = rc;
+        if (colvalid && (((j - 1) & 7) == 7 || j == W)) {
+#pragma unroll
+          for (int k = 0; k < LONG_K; ++k) if (k < nact) { drow[(size_t)k * wpr + ((j - 1) >> 3)] = wd[k]; wd[k] = 0u; }
+        }
+        if (lane == 31 && colvalid) { Hb[j] = out_h; Fb[j] = out_f; }   // boundary for the next stripe (lane 0 is 31 columns ahead: in place)
       }
       __syncwarp();
     }
