@@ -675,3 +675,45 @@ def test_cfg5_shape_through_the_multi_gpu_driver():
         one = a.align(w.reads, w.windows, w.pair_ref_idx)
     for f in FIELDS + ("cigar_n", "flags"):
         assert np.array_equal(one.results[f], r[f]), f
+
+
+def test_streamed_and_multi_gpu_batches_with_contig_sized_reads(monkeypatch):
+    """A large batch (streamed through the slots inside ubu_sw_align_batch, and sharded by ubu_sw_multi_align) that also holds contig-sized
+    reads: the chunks plan their long reads onto sw_long_kernel; records must equal the one-shot call's, and the long ones the oracle's."""
+    from ubu_b200 import multi as M
+
+    rng = np.random.default_rng(41)
+    n_short, L, W = 150_000, 100, 600
+    wins = rng.integers(0, 4, size=(n_short // 3, W), dtype=np.uint8)
+    idx = np.sort(rng.integers(0, wins.shape[0], size=n_short)).astype(np.uint32)
+    start = rng.integers(0, W - L, size=n_short)
+    reads = [wins[idx[k], start[k]:start[k] + L].copy() for k in range(n_short)]
+    long_at = list(range(500, n_short, 3000))                                 # 50 long reads spread over the batch
+    big = rng.integers(0, 4, size=2500, dtype=np.uint8)
+    for t in long_at:
+        a = int(rng.integers(0, 400)); b = int(rng.integers(300, 1500))
+        r = np.concatenate([big[a:a + b // 2], big[a + b // 2 + 7:a + b]])        # a 7 bp deletion
+        reads[t] = r
+    wl = [w for w in wins]
+    win_of = idx.copy()
+    for t in long_at:                                                           # the long reads get the big window, appended to the set
+        win_of[t] = len(wl)
+    wl.append(big)
+    # keep window indices ascending enough for streaming: the big window sits at the end, so chunks holding a long read fall back
+    rs, ws = U.pack_codes(reads), U.pack_codes(wl)
+    with U.SwAligner(slots=4) as a:
+        got = a.align(rs, ws, win_of)
+        monkeypatch.setenv("UBU_NO_STREAM", "1")
+        want = a.align(rs, ws, win_of)
+        monkeypatch.delenv("UBU_NO_STREAM")
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(got.results[f], want.results[f]), f
+    ores, ocig = O.align_batch([reads[t] for t in long_at], [big] * len(long_at), None, nthreads=8)
+    for j, t in enumerate(long_at):
+        assert all(int(got.results[t][f]) == int(ores[j][f]) for f in FIELDS) and got.cigar(t) == ocig[j] == want.cigar(t)
+        assert any(op == 2 for _, op in got.cigar(t))
+    with M.MultiAligner(chunk=20_000) as m:
+        mg = m.align(rs, ws, win_of)
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(mg.results[f], want.results[f]), f
+    assert all(mg.cigar(t) == want.cigar(t) for t in long_at)
