@@ -657,7 +657,11 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   const int max_rows = std::max(s.lmax, 1);
   const size_t NS = s.n_slots;
   // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
-  static const bool tb_serial = env_off("UBU_TB_SERIAL");     // development switch: every traceback kernel on the main stream
+  // The traceback kernels of a batch are independent and run side by side on the slot's side streams; that hides their tails and pays
+  // on batches up to ~1M tasks (cfg2: 0.47 vs 0.65 ms, cfg4: 7.3 vs 7.8 ms). On very large batches every kernel fills the GPU by itself
+  // and the store-heavy ones only compete for HBM (cfg3, 5M tasks: 9.6 ms side by side, 8.2 ms one after the other): those run in turn.
+  static const bool tb_serial_env = env_off("UBU_TB_SERIAL");  // development switch: always one after the other
+  const bool tb_serial = tb_serial_env || s.n_tasks >= (3u << 20);
   cudaStream_t ax[kAux];
   for (int k = 0; k < kAux; ++k) ax[k] = tb_serial ? st : s.aux[k];
   CU(h, cudaEventRecord(s.ev_fork, st));
