@@ -385,7 +385,7 @@ __device__ __forceinline__ void build_selectors(const TaskView& ta, const TaskVi
 }
 
 // One packed band cell. Returns the value to store: H | (diagonal does not reproduce H) << 15, per half.
-template <bool HAS_N>
+template <bool HAS_N, bool WITH_FLAG = true>
 __device__ __forceinline__ uint32_t band_cell(uint32_t pa, uint32_t pb, uint32_t selv, uint32_t diag_hoe, uint32_t up_hoe, uint32_t up_f,
                                               uint32_t& e, uint32_t& hoe_left, uint32_t& f_out, uint32_t NEG_OE, uint32_t NEG_EXT,
                                               uint32_t POS_OE) {
@@ -397,6 +397,7 @@ __device__ __forceinline__ uint32_t band_cell(uint32_t pa, uint32_t pb, uint32_t
   const uint32_t h = __vimax3_s16x2_relu(t, e, f);
   hoe_left = __vadd2(h, NEG_OE);
   f_out = f;
+  if (!WITH_FLAG) return h;                                                 // byte store: H only, the walk tests the diagonal from the sequences
   const uint32_t notdiag = __vmins2(__vsub2(h, t), 0x00010001u);           // h >= t always: 0 iff the diagonal reproduces H
   return h + notdiag * 0x8000u;
 }
@@ -405,7 +406,11 @@ __device__ __forceinline__ uint32_t band_cell(uint32_t pa, uint32_t pb, uint32_t
 // hstore: one contiguous block per warp, packed value of band cell (n, b) of lane l at block[(n*BW + b) * 32 + l]: a warp's
 //         store is one 128-byte line, consecutive cells are adjacent (streaming writes, TLB-friendly walk reads)
 // selectors: shared memory, sel[k * THREADS + tid], k = n + b
-template <int BW, bool HAS_N, int THREADS>
+// BYTES = 2: 16 bits per task and cell, H | not-diagonal flag << 15, the walk needs no sequence access.
+// BYTES = 1: when no score of the batch can exceed 255 (H <= S <= match * L), H alone in one byte, two cells per word (bytes A_b, A_b+1,
+//            B_b, B_b+1): half the store traffic -- these kernels are bound by HBM writes -- and three instructions less per cell; the walk
+//            then tests the diagonal from the sequences, 16 bases per load, as the strip kernel's does.
+template <int BW, bool HAS_N, int THREADS, int BYTES>
 __global__ void __launch_bounds__(THREADS)
 tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
                    uint32_t* __restrict__ hstore, int max_rows) {
@@ -420,7 +425,8 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
   const uint32_t NEG_OE = a.sc.neg_oe2, NEG_EXT = a.sc.neg_ext2, POS_OE = a.sc.pos_oe2;
   uint32_t opbuf[BW + 8];
-  uint32_t* hmine = hstore + (size_t)(gtid >> 5) * ((size_t)max_rows * BW * 32) + (gtid & 31u);
+  constexpr int WPR = BYTES == 1 ? BW / 2 : BW;                 // words per band row and lane
+  uint32_t* hmine = hstore + (size_t)(gtid >> 5) * ((size_t)max_rows * WPR * 32) + (gtid & 31u);
 
   for (uint32_t pair = gtid; pair < n_pairs; pair += nthreads) {
     const uint32_t tA = list[2u * pair];
@@ -442,18 +448,28 @@ tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned i
       const uint32_t pb = rb.template profile<HAS_N>(n, MM4, MX, N4);
       uint32_t e = NEG_OE, hoe_left = NEG_OE;
       const SelT* srow = sel + (size_t)n * THREADS + tid;
-      uint32_t* hrow = hmine + (size_t)n * BW * 32;
+      uint32_t* hrow = hmine + (size_t)n * WPR * 32;
+      uint32_t even = 0u;
 #pragma unroll
       for (int b = 0; b < BW; ++b) {
         const uint32_t up_hoe = (b + 1 < BW) ? Hd[b + 1] : NEG_OE, up_f = (b + 1 < BW) ? Fv[b + 1] : NEG_OE;
         uint32_t f;
-        hrow[b * 32] = band_cell<HAS_N>(pa, pb, srow[b * THREADS], Hd[b], up_hoe, up_f, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
+        const uint32_t v = band_cell<HAS_N, BYTES == 2>(pa, pb, srow[b * THREADS], Hd[b], up_hoe, up_f, e, hoe_left, f, NEG_OE, NEG_EXT, POS_OE);
+        if (BYTES == 2) hrow[b * 32] = v;
+        else if (b & 1) hrow[(b >> 1) * 32] = v * 256u + even;   // bytes (A_b-1, A_b, B_b-1, B_b): one multiply-add on the FMA pipe
+        else even = v;
         Hd[b] = hoe_left; Fv[b] = f;
       }
     }
-    walk_h_and_emit<HAS_N, true, 8>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
-    if (haveB)
-      walk_h_and_emit<HAS_N, true, 8>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
+    if (BYTES == 2) {
+      walk_h_and_emit<HAS_N, true, 8>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] & 0xFFFFu; });
+      if (haveB)
+        walk_h_and_emit<HAS_N, true, 8>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return hmine[(n * BW + b) * 32] >> 16; });
+    } else {
+      walk_h_and_emit<HAS_N, false, 8>(a, tA, va, ga, BW, opbuf, [&](int n, int b) -> uint32_t { return (hmine[(n * WPR + (b >> 1)) * 32] >> (8 * (b & 1))) & 0xFFu; });
+      if (haveB)
+        walk_h_and_emit<HAS_N, false, 8>(a, tB, vb, gb, BW, opbuf, [&](int n, int b) -> uint32_t { return (hmine[(n * WPR + (b >> 1)) * 32] >> (16 + 8 * (b & 1))) & 0xFFu; });
+    }
   }
 }
 

@@ -675,8 +675,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
                  sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
     uint32_t *h8 = s.d_hstore.p + s.h_off[0], *h16 = s.d_hstore.p + s.h_off[1], *h32 = s.d_hstore.p + s.h_off[2];
-    if (s.any_n) {
-      auto k8 = tb_fill_reg_kernel<8, true, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, true, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, true, TB_THREADS>;
+    static const bool reg16 = env_off("UBU_TB_REG16");            // development switch: the 16-bit store + flag form whatever the scores
+    const bool hbyte = h->sc.match * max_rows <= 255 && !reg16;  // no score of the batch exceeds 255: one byte per stored H
+    auto launch3 = [&](auto k8, auto k16, auto k32) -> int {
       if (sm32 > 48 * 1024) {
         CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
@@ -685,17 +686,14 @@ int do_run(ubu_sw_handle* h, Slot& s) {
       k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
       k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
       k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
-    } else {
-      auto k8 = tb_fill_reg_kernel<8, false, TB_THREADS>; auto k16 = tb_fill_reg_kernel<16, false, TB_THREADS>; auto k32 = tb_fill_reg_kernel<32, false, TB_THREADS>;
-      if (sm32 > 48 * 1024) {
-        CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      }
-      k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
-    }
+      return UBU_SW_OK;
+    };
+    int rc3;
+    if (s.any_n && hbyte) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 1>, tb_fill_reg_kernel<16, true, TB_THREADS, 1>, tb_fill_reg_kernel<32, true, TB_THREADS, 1>);
+    else if (s.any_n) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 2>, tb_fill_reg_kernel<16, true, TB_THREADS, 2>, tb_fill_reg_kernel<32, true, TB_THREADS, 2>);
+    else if (hbyte) rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 1>, tb_fill_reg_kernel<16, false, TB_THREADS, 1>, tb_fill_reg_kernel<32, false, TB_THREADS, 1>);
+    else rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 2>, tb_fill_reg_kernel<16, false, TB_THREADS, 2>, tb_fill_reg_kernel<32, false, TB_THREADS, 2>);
+    if (rc3) return rc3;
     s.n_launches += 3;
   }
   for (int k = 1; k >= 0; --k) {                       // wide bands: the rare very wide ones first, then the common widths
