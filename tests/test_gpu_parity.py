@@ -234,6 +234,19 @@ def test_cfg4_120k_every_record_with_tie_stress(aligner):
     assert int(res["cigar_n"].max()) >= 7                      # gapped CIGARs are in the set
 
 
+def test_cfg4_300k_resident_batch_runs_its_traceback_in_phases(aligner):
+    """A large mixed-length batch through stage / run / fetch: ubu_sw_run cuts its forward launches into groups and runs the traceback
+    of each group underneath the next group's forward pass (list ranges from counter snapshots). Every record and CIGAR vs the oracle,
+    twice (the second run reuses the slot's counters and scratch)."""
+    w = WL.cfg4(300_000, tie_stress=6_000, seed=77)
+    aligner.stage(0, w.reads, w.windows, w.pair_ref_idx)
+    for _ in range(2):
+        aligner.run(0); aligner.sync(0)
+        assert aligner.last_run_launches(0) >= 16 + 2 * 7         # forward launches + two traceback phases of 7 kernels
+        al = aligner.fetch(0, w.n_tasks)
+        check_every_record_fast(al, w)
+
+
 def test_extreme_scoring_reaches_the_scalar_last_resort():
     """match 31 / ext 1 lets a low score afford thousands of gap bases: the band outgrows every packed class."""
     rng = np.random.default_rng(2)

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--check", type=int, default=2000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--only", default="")
+    ap.add_argument("--flush", action="store_true", help="write a 512 MB buffer before every timed run (cold L2, as bench.py does)")
     a = ap.parse_args()
     cfgs = {
         "cfg1": lambda: WL.cfg1(10_000),
@@ -52,6 +53,9 @@ def main():
     }
     threads = os.cpu_count() or 1
     out = []
+    if a.flush:
+        import torch
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda:0")
     with U.SwAligner(device=0, slots=2) as al:
         for name, make in cfgs.items():
             if a.only and name not in a.only.split(","):
@@ -61,6 +65,8 @@ def main():
             al.run(0); al.sync(0)
             ms = []
             for _ in range(a.steps):
+                if a.flush:
+                    flush.zero_(); torch.cuda.synchronize()
                 al.run(0); al.sync(0); ms.append(al.last_run_ms(0))
             m = np.mean(np.array(ms), axis=0)
             res = al.fetch(0, w.n_tasks)

@@ -249,9 +249,10 @@ __device__ __forceinline__ void walk_h_and_emit(const TbArgs& a, uint32_t task, 
 // backwards from (i, je); the first time the sum reaches S the running H hits 0 (SPEC stop).
 template <bool HAS_N>
 __global__ void __launch_bounds__(128)
-tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count) {
+tb_diag_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ first, const unsigned int* __restrict__ count) {
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n = *count;
+  const uint32_t n = *count - *first;                  // this launch serves list[*first, *count) (see do_run: traceback phases)
+  list += *first;
   const int ma = a.sc.match, mm = a.sc.mismatch;
   for (uint32_t idx = gtid; idx < n; idx += nthreads) {
     const uint32_t task = list[idx];
@@ -412,14 +413,15 @@ __device__ __forceinline__ uint32_t band_cell(uint32_t pa, uint32_t pb, uint32_t
 //            then tests the diagonal from the sequences, 16 bases per load, as the strip kernel's does.
 template <int BW, bool HAS_N, int THREADS, int BYTES>
 __global__ void __launch_bounds__(THREADS)
-tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
+tb_fill_reg_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ first, const unsigned int* __restrict__ count,
                    uint32_t* __restrict__ hstore, int max_rows) {
   using SelT = typename SelType<HAS_N>::type;
   extern __shared__ __align__(16) unsigned char tb_smem[];
   SelT* sel = reinterpret_cast<SelT*>(tb_smem);
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int tid = threadIdx.x;
-  const uint32_t n_tasks = *count, n_pairs = (n_tasks + 1u) / 2u;
+  const uint32_t n_tasks = *count - *first, n_pairs = (n_tasks + 1u) / 2u;
+  list += *first;
   const int oe = a.sc.gap_open + a.sc.gap_ext;
   const uint32_t mmb = (uint32_t)(a.sc.mismatch + oe) & 0xFFu, mab = (uint32_t)(a.sc.match + oe) & 0xFFu;
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
@@ -485,10 +487,11 @@ __host__ __device__ inline size_t tb_wide_scratch_bytes(int max_rows, int bw_cap
 }
 
 __global__ void __launch_bounds__(64)
-tb_wide_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ count,
+tb_wide_kernel(TbArgs a, const uint32_t* __restrict__ list, const unsigned int* __restrict__ first, const unsigned int* __restrict__ count,
                unsigned char* __restrict__ scratch, int max_rows, int bw_cap) {
   const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n = *count;
+  const uint32_t n = *count - *first;
+  list += *first;
   const int ma = a.sc.match, mm = a.sc.mismatch, ext = a.sc.gap_ext, oe = a.sc.gap_open + a.sc.gap_ext;
   const size_t per = tb_wide_scratch_bytes(max_rows, bw_cap);
   unsigned char* mine = scratch + (size_t)gtid * per;

@@ -52,6 +52,7 @@ __host__ __device__ inline size_t tbs_boundary_bytes_per_warp(int rows_cap, int 
 
 struct StripArgs {
   const uint32_t* lists;          // [TB_CLASSES][n_slots]
+  const unsigned int* firsts;     // [TB_CLASSES] this launch serves lists[c][firsts[c], counts[c])
   const unsigned int* counts;     // [TB_CLASSES]
   unsigned int* work;             // unit counter of this launch (zeroed before it)
   int cls_lo, cls_hi;             // traceback classes served (a launch for the common widths, one for the rare very wide bands)
@@ -87,20 +88,20 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
 
   // units of 32 pairs over the classes this launch serves, widest class first
   unsigned int total_units = 0;
-  for (int c = sa.cls_hi; c >= sa.cls_lo; --c) total_units += ((sa.counts[c] + 1u) / 2u + 31u) / 32u;
+  for (int c = sa.cls_hi; c >= sa.cls_lo; --c) total_units += ((sa.counts[c] - sa.firsts[c] + 1u) / 2u + 31u) / 32u;
 
   for (;;) {
     unsigned int unit = 0;
     if (lane == 0) unit = atomicAdd(sa.work, 1u);
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= total_units) break;
-    int cls = sa.cls_hi; unsigned int ubase = 0, n_tasks = sa.counts[cls];
+    int cls = sa.cls_hi; unsigned int ubase = 0, n_tasks = sa.counts[cls] - sa.firsts[cls];
     for (;;) {                                                   // the class this unit falls into
       const unsigned int nu = ((n_tasks + 1u) / 2u + 31u) / 32u;
       if (unit < ubase + nu || cls == sa.cls_lo) break;
-      ubase += nu; --cls; n_tasks = sa.counts[cls];
+      ubase += nu; --cls; n_tasks = sa.counts[cls] - sa.firsts[cls];
     }
-    const uint32_t* list = sa.lists + (size_t)cls * sa.n_slots;
+    const uint32_t* list = sa.lists + (size_t)cls * sa.n_slots + sa.firsts[cls];
     const unsigned int n_pairs = (n_tasks + 1u) / 2u;
     const unsigned int pair = (unit - ubase) * 32u + (unsigned)lane;
     const bool have = pair < n_pairs, haveB = have && 2u * pair + 1u < n_tasks;

@@ -41,7 +41,12 @@ constexpr int TB_THREADS = 128, TB_GRID_PER_SM = 3;      // register-band traceb
 constexpr int TBS_GRID_PER_SM = UBU_TBS_MIN_BLOCKS;      // wide bands: row strips in registers, one thread per task pair (sw_tbstrip.cuh)
 constexpr int kStripBwCap = TBS_BW_MAX;                  // widest band the strip kernel takes: every band default scoring allows for reads <= 256 bp
 constexpr size_t kStripScratchBudget = (size_t)6 << 30;  // per pipeline slot; fewer CTAs are launched when a batch's worst case would need more
-constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, two strip work counters
+constexpr int CTR_CIG = TB_CLASSES, CTR_ERR = TB_CLASSES + 1, CTR_WORK = TB_CLASSES + 2;   // d_ctr: class counts, CIGAR cursor, error flags, work counters (+2: long reads)
+constexpr int kTbPhases = 8;                       // traceback phases of a large batch (do_run)
+constexpr int CTR_SNAP = 16;                       // [16 * g, +TB_CLASSES): class counts after forward group g (g < kTbPhases - 1)
+constexpr int CTR_ZERO = 16 * kTbPhases;           // TB_CLASSES zeros: the first phase's list starts
+constexpr int CTR_STRIP_WORK = CTR_ZERO + 16;      // [2 * phase + launch] unit counters of the strip kernel's launches
+constexpr int CTR_WORDS = CTR_STRIP_WORK + 2 * kTbPhases + 8;
 constexpr int kStripBwCommon = 120;                      // bands up to this width go to the full-grid strip launch (TB classes 4..7)
 constexpr int TBW_THREADS = 64, TBW_GRID_PER_SM = 2;     // scalar last resort
 constexpr int kMaxK = 20;                                // largest K in UBU_FWD_CFGS: i_hi - i_lo <= kMaxK - 1
@@ -540,7 +545,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
   if (idx) CU(h, s.d_idx.reserve(n));
   CU(h, s.d_order.reserve(s.n_slots + s.long_tasks.size())); CU(h, s.d_lists.reserve((size_t)TB_CLASSES * s.n_slots));
   CU(h, s.d_fwd.reserve(n)); CU(h, s.d_res.reserve(n));
-  CU(h, s.d_ctr.reserve(64)); CU(h, s.h_ctr.reserve(16));
+  CU(h, s.d_ctr.reserve(CTR_WORDS)); CU(h, s.h_ctr.reserve(16));
   if (s.cig_cap < 6u * n + 4096u) { s.cig_cap = 6u * n + 4096u; }
   CU(h, s.d_cig.reserve(s.cig_cap));
   // traceback scratch
@@ -636,7 +641,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   s.n_launches = 0;
   CU(h, cudaEventRecord(s.ev[0], st));
   if (s.n_tasks == 0) { CU(h, cudaEventRecord(s.ev[1], st)); CU(h, cudaEventRecord(s.ev[2], st)); s.ran = true; return UBU_SW_OK; }
-  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, 16 * sizeof(unsigned int), st));
+  CU(h, cudaMemsetAsync(s.d_ctr.p, 0, CTR_WORDS * sizeof(unsigned int), st));
   // (a streamed chunk keeps absolute offsets and window indices: the pointers are moved back instead, see Slot::bias_*)
   DevSeqs reads{s.d_rp.p - s.bias_rp, s.d_roff.p, s.d_rlen.p, s.reads_n ? s.d_rn.p - s.bias_rn : nullptr, s.reads_n ? s.d_rnoff.p : nullptr};
   DevSeqs wins{s.d_wp.p - s.bias_wp, s.d_woff.p - s.bias_w, s.d_wlen.p - s.bias_w, s.wins_n ? s.d_wn.p - s.bias_wn : nullptr,
@@ -645,72 +650,109 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   const uint32_t* d_order = s.identity_order ? nullptr : s.d_order.p;
   // the forward kernels' epilogue also sorts the tasks into the traceback class lists (and finishes unaligned ones)
   const TbPlan plan{s.caps, s.d_res.p, s.d_lists.p, s.d_ctr.p, s.n_slots};
-  for (const FwdLaunch& L : s.launches) {
-    CU(h, launch_fwd(L, reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, plan, st));
-    ++s.n_launches;
-  }
-  CU(h, cudaEventRecord(s.ev[1], st));
-
   TbArgs a;
   a.reads = reads; a.wins = wins; a.ref_idx = idx; a.sc = h->sc; a.fwd = s.d_fwd.p; a.res = s.d_res.p;
   a.cig_pool = s.d_cig.p; a.cig_cap = s.cig_cap; a.cig_cursor = s.d_ctr.p + CTR_CIG; a.err_flag = s.d_ctr.p + CTR_ERR; a.cig_base = s.cig_base;
   const int max_rows = std::max(s.lmax, 1);
   const size_t NS = s.n_slots;
-  // fork: [diagonal scan] on the main stream, [band 8, band 16] / [band 32] / [shared-memory band, scalar] on side streams
-  // The traceback kernels of a batch are independent and run side by side on the slot's side streams; that hides their tails and pays
-  // on batches up to ~1M tasks (cfg2: 0.47 vs 0.65 ms, cfg4: 7.3 vs 7.8 ms). On very large batches every kernel fills the GPU by itself
-  // and the store-heavy ones only compete for HBM (cfg3, 5M tasks: 9.6 ms side by side, 8.2 ms one after the other): those run in turn.
+
+  // Traceback phases. The class lists grow in launch order, and a traceback kernel at a third of its grid loses little (it is bound by
+  // HBM writes) while it leaves most of each SM to the forward kernels (bound by integer issue). On large mixed-length batches (many
+  // forward launches) the launches are cut into groups of about equal cell count, and the traceback of group g (list entries [counts
+  // after group g-1, counts after group g), from counter snapshots taken in stream order) runs on the side streams, at a third of its
+  // grid, underneath the forward launches of group g+1; only the last group's traceback stays exposed (cfg4, 1M reads: 25.6 - 28.9 ms
+  // box to box -> 24.6 ms). Batches with one or a few forward launches run unphased: with 2 launches cfg3 gains 0.7 % and cfg2+N loses
+  // 3 % (a reduced-grid phase outlives the short forward launch behind it), profiles/tb_phases_r02.txt.
+  static const int phases_env = [] { const char* v = getenv("UBU_TB_PHASES"); return v && *v ? std::max(1, std::min(kTbPhases, atoi(v))) : 0; }();
+  static const int gdiv_env = [] { const char* v = getenv("UBU_TB_PHASE_GRID_DIV"); return v && *v ? std::max(1, atoi(v)) : 3; }();
+  int n_phases = 1;
+  if (phases_env) { if (s.launches.size() > 1) n_phases = std::min<int>(phases_env, (int)s.launches.size()); }   // development switch
+  else if (s.n_tasks >= (256u << 10) && s.launches.size() >= 8)
+    n_phases = (int)std::min<size_t>(std::min<size_t>(kTbPhases, s.launches.size() / 2), s.n_tasks >> 17);
+  std::vector<size_t> phase_end(n_phases, s.launches.size());         // phase g = launches [phase_end[g-1], phase_end[g])
+  if (n_phases > 1) {
+    double total = 0, acc = 0;
+    auto cost = [&](const FwdLaunch& L) { return (double)L.n_slots * kFwdCfgs[L.cfg].lmax * std::max(L.wmax, 1); };
+    for (const FwdLaunch& L : s.launches) total += cost(L);
+    int g = 0;
+    for (size_t i = 0; i < s.launches.size() && g + 1 < n_phases; ++i) {
+      acc += cost(s.launches[i]);
+      if (acc >= total * (g + 1) / n_phases) phase_end[g++] = i + 1;
+    }
+    if (g > 0 && phase_end[g - 1] == s.launches.size()) --g;        // no forward launch left for a last group
+    n_phases = g + 1; phase_end.resize(n_phases); phase_end[n_phases - 1] = s.launches.size();
+  }
+  // traceback kernels side by side on the side streams hide their tails and pay on batches up to ~1M tasks (cfg2: 0.47 vs 0.65 ms,
+  // cfg4: 7.3 vs 7.8 ms). On very large batches every kernel fills the GPU by itself and the store-heavy ones only compete for HBM
+  // (cfg3, 5M tasks: 9.6 ms side by side, 8.2 ms one after the other): those run in turn, on one stream.
   static const bool tb_serial_env = env_off("UBU_TB_SERIAL");  // development switch: always one after the other
   const bool tb_serial = tb_serial_env || s.n_tasks >= (3u << 20);
-  cudaStream_t ax[kAux];
-  for (int k = 0; k < kAux; ++k) ax[k] = tb_serial ? st : s.aux[k];
-  CU(h, cudaEventRecord(s.ev_fork, st));
-  for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
-  if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
-  else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, st>>>(a, s.d_lists.p, s.d_ctr.p + 0);
-  CU(h, cudaGetLastError()); ++s.n_launches;
-  {
-    const int grid = s.tb_grid;
-    const size_t selsz = s.any_n ? 4 : 2;
-    const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
-                 sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
-    uint32_t *h8 = s.d_hstore.p + s.h_off[0], *h16 = s.d_hstore.p + s.h_off[1], *h32 = s.d_hstore.p + s.h_off[2];
-    static const bool reg16 = env_off("UBU_TB_REG16");            // development switch: the 16-bit store + flag form whatever the scores
-    const bool hbyte = h->sc.match * max_rows <= 255 && !reg16;  // no score of the batch exceeds 255: one byte per stored H
-    auto launch3 = [&](auto k8, auto k16, auto k32) -> int {
-      if (sm32 > 48 * 1024) {
-        CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-      }
-      k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, s.d_ctr.p + 1, h8, max_rows); CU(h, cudaGetLastError());
-      k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, s.d_ctr.p + 2, h16, max_rows); CU(h, cudaGetLastError());
-      k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, s.d_ctr.p + 3, h32, max_rows); CU(h, cudaGetLastError());
-      return UBU_SW_OK;
-    };
-    int rc3;
-    if (s.any_n && hbyte) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 1>, tb_fill_reg_kernel<16, true, TB_THREADS, 1>, tb_fill_reg_kernel<32, true, TB_THREADS, 1>);
-    else if (s.any_n) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 2>, tb_fill_reg_kernel<16, true, TB_THREADS, 2>, tb_fill_reg_kernel<32, true, TB_THREADS, 2>);
-    else if (hbyte) rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 1>, tb_fill_reg_kernel<16, false, TB_THREADS, 1>, tb_fill_reg_kernel<32, false, TB_THREADS, 1>);
-    else rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 2>, tb_fill_reg_kernel<16, false, TB_THREADS, 2>, tb_fill_reg_kernel<32, false, TB_THREADS, 2>);
-    if (rc3) return rc3;
-    s.n_launches += 3;
+  const bool phased = n_phases > 1;
+  cudaStream_t ax[kAux], dg;                                    // dg: the diagonal class
+  for (int k = 0; k < kAux; ++k) ax[k] = tb_serial ? (phased ? s.aux[0] : st) : s.aux[k];
+  dg = phased ? ax[0] : st;
+  const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
+  const size_t selsz = s.any_n ? 4 : 2;
+  const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
+               sm32 = (size_t)(max_rows + 32) * TB_THREADS * selsz;
+  uint32_t *h8 = s.d_hstore.p + s.h_off[0], *h16 = s.d_hstore.p + s.h_off[1], *h32 = s.d_hstore.p + s.h_off[2];
+  static const bool reg16 = env_off("UBU_TB_REG16");            // development switch: the 16-bit store + flag form whatever the scores
+  const bool hbyte = h->sc.match * max_rows <= 255 && !reg16;  // no score of the batch exceeds 255: one byte per stored H
+
+  size_t li = 0;
+  for (int g = 0; g < n_phases; ++g) {
+    for (; li < phase_end[g]; ++li) {
+      CU(h, launch_fwd(s.launches[li], reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, plan, st));
+      ++s.n_launches;
+    }
+    const bool last = g + 1 == n_phases;
+    const int gdiv = last ? 1 : gdiv_env;
+    const int grid = std::max(1, s.tb_grid / gdiv);
+    // list ranges of this phase: [first, count) per class
+    const unsigned int* first = g == 0 ? s.d_ctr.p + CTR_ZERO : s.d_ctr.p + CTR_SNAP + 16 * (g - 1);
+    const unsigned int* count = last ? s.d_ctr.p : s.d_ctr.p + CTR_SNAP + 16 * g;
+    if (!last) CU(h, cudaMemcpyAsync(s.d_ctr.p + CTR_SNAP + 16 * g, s.d_ctr.p, TB_CLASSES * sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+    if (last) CU(h, cudaEventRecord(s.ev[1], st));
+    CU(h, cudaEventRecord(s.ev_fork, st));
+    for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
+    if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, dg>>>(a, s.d_lists.p, first, count);
+    else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, dg>>>(a, s.d_lists.p, first, count);
+    CU(h, cudaGetLastError()); ++s.n_launches;
+    {
+      auto launch3 = [&](auto k8, auto k16, auto k32) -> int {
+        if (sm32 > 48 * 1024) {
+          CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+          CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+          CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        }
+        k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError());
+        k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError());
+        k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, first + 3, count + 3, h32, max_rows); CU(h, cudaGetLastError());
+        return UBU_SW_OK;
+      };
+      int rc3;
+      if (s.any_n && hbyte) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 1>, tb_fill_reg_kernel<16, true, TB_THREADS, 1>, tb_fill_reg_kernel<32, true, TB_THREADS, 1>);
+      else if (s.any_n) rc3 = launch3(tb_fill_reg_kernel<8, true, TB_THREADS, 2>, tb_fill_reg_kernel<16, true, TB_THREADS, 2>, tb_fill_reg_kernel<32, true, TB_THREADS, 2>);
+      else if (hbyte) rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 1>, tb_fill_reg_kernel<16, false, TB_THREADS, 1>, tb_fill_reg_kernel<32, false, TB_THREADS, 1>);
+      else rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 2>, tb_fill_reg_kernel<16, false, TB_THREADS, 2>, tb_fill_reg_kernel<32, false, TB_THREADS, 2>);
+      if (rc3) return rc3;
+      s.n_launches += 3;
+    }
+    for (int k = 1; k >= 0; --k) {                       // wide bands: the rare very wide ones first, then the common widths
+      const Slot::StripLaunch& L = s.strip[k];
+      if (L.grid <= 0) continue;
+      StripArgs sa;
+      sa.lists = s.d_lists.p; sa.firsts = first; sa.counts = count; sa.work = s.d_ctr.p + CTR_STRIP_WORK + 2 * g + k; sa.n_slots = s.n_slots;
+      sa.cls_lo = L.cls_lo; sa.cls_hi = L.cls_hi;
+      sa.hstore = s.d_strip.p + L.h_off; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + L.b_off);
+      sa.rows_cap = s.caps.rows_cap; sa.bw_cap = L.bw_cap;
+      CU(h, launch_strip(s.any_n, def, s.strip_bytes, std::max(1, L.grid / gdiv), a, sa, k == 0 ? ax[2] : ax[3]));
+      ++s.n_launches;
+    }
+    tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[1]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, first + TB_CLASS_SCALAR, count + TB_CLASS_SCALAR,
+                                                            s.d_wide.p, max_rows, s.bw_cap);
+    CU(h, cudaGetLastError()); ++s.n_launches;
   }
-  for (int k = 1; k >= 0; --k) {                       // wide bands: the rare very wide ones first, then the common widths
-    const Slot::StripLaunch& L = s.strip[k];
-    if (L.grid <= 0) continue;
-    const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
-    StripArgs sa;
-    sa.lists = s.d_lists.p; sa.counts = s.d_ctr.p; sa.work = s.d_ctr.p + CTR_WORK + k; sa.n_slots = s.n_slots;
-    sa.cls_lo = L.cls_lo; sa.cls_hi = L.cls_hi;
-    sa.hstore = s.d_strip.p + L.h_off; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + L.b_off);
-    sa.rows_cap = s.caps.rows_cap; sa.bw_cap = L.bw_cap;
-    CU(h, launch_strip(s.any_n, def, s.strip_bytes, L.grid, a, sa, k == 0 ? ax[2] : ax[3]));
-    ++s.n_launches;
-  }
-  tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[1]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, s.d_ctr.p + TB_CLASS_SCALAR,
-                                                          s.d_wide.p, max_rows, s.bw_cap);
-  CU(h, cudaGetLastError()); ++s.n_launches;
   if (s.long_grid > 0) {                              // contig-sized queries (L > 256): forward, direction matrix and walk in one kernel
     LongArgs la;
     la.list = s.d_order.p + s.n_slots; la.n = (uint32_t)s.long_tasks.size(); la.work = s.d_ctr.p + CTR_WORK + 2;
@@ -829,13 +871,17 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
   h->device = device; h->n_slots = slots; h->sm_count = prop.multiProcessorCount;
   h->sc = make_scoring(p.match, p.mismatch, p.gap_open, p.gap_ext);
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return UBU_SW_ERR_CUDA; }
+  int prio_lo = 0, prio_hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_lo = prio_hi = 0; }
+  if (env_off("UBU_TB_NOPRIO")) prio_hi = prio_lo;              // development switch
   for (int i = 0; i < slots; ++i) {
-    if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&h->slots[i].stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     for (int e = 0; e < 3; ++e)
       if (cudaEventCreate(&h->slots[i].ev[e]) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&h->slots[i].ev_fork, cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     for (int e = 0; e < kAux; ++e) {
-      if (cudaStreamCreateWithFlags(&h->slots[i].aux[e], cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+      // side streams above the main stream's priority: a traceback phase running underneath later forward launches gets its CTAs placed
+      if (cudaStreamCreateWithPriority(&h->slots[i].aux[e], cudaStreamNonBlocking, prio_hi) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
       if (cudaEventCreateWithFlags(&h->slots[i].ev_join[e], cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     }
   }
