@@ -394,12 +394,34 @@ def run_configs(al, peak_gcups: float, steps: int, flush, torch, threads: int):
         res = al.fetch(0, w.n_tasks)
         nchk, bad = oracle_sample_check(w, res, n_check, threads)
         value = w.cells / (m[0] * 1e-3) / 1e9
+        launches = al.last_run_launches(0)
+        # a batch whose traceback ran in phases underneath its forward launches: time the same staged batch once more
+        # with the phases switched off, for the forward / traceback split of the kernels on their own (reported, not the value)
+        split = None
+        if name == "cfg4":
+            os.environ["UBU_TB_PHASES"] = "1"
+            try:
+                al.run(0); al.sync(0)
+                ms1 = []
+                for _ in range(steps):
+                    flush.zero_(); torch.cuda.synchronize()
+                    al.run(0); al.sync(0); ms1.append(al.last_run_ms(0))
+                m1 = np.mean(np.array(ms1), axis=0)
+                split = {"ms_per_step": float(m1[0]), "fwd_ms": float(m1[1]), "traceback_ms": float(m1[2]),
+                         "launches_per_step": al.last_run_launches(0)}
+            finally:
+                del os.environ["UBU_TB_PHASES"]
+        fwd_alone = split["fwd_ms"] if split else m[1]
         out[name] = {"workload": desc, "tasks": w.n_tasks, "cells": int(w.cells), "value": value, "unit": "GCUPS",
                      "reads_per_s": w.n_tasks / (m[0] * 1e-3), "ms_per_step": float(m[0]), "fwd_ms": float(m[1]), "traceback_ms": float(m[2]),
-                     "steps": steps, "launches_per_step": al.last_run_launches(0), "dominant_kernel": CONFIG_KERNELS[name],
+                     "steps": steps, "launches_per_step": launches, "dominant_kernel": CONFIG_KERNELS[name],
                      "roofline": {"bound": "int_alu", "peak": peak_gcups, "unit": "GCUPS", "frac": value / peak_gcups,
-                                  "fwd_only_frac": w.cells / (m[1] * 1e-3) / 1e9 / peak_gcups},
+                                  "fwd_only_frac": w.cells / (fwd_alone * 1e-3) / 1e9 / peak_gcups},
                      "oracle_check": {"checked": nchk, "mismatching": bad}, "gen_s": round(gen_s, 1)}
+        if split:
+            out[name]["traceback_phases"] = ("fwd_ms holds the forward launches WITH the traceback of earlier groups underneath, traceback_ms the "
+                                             "exposed rest; 'unphased' = the same batch with UBU_TB_PHASES=1")
+            out[name]["unphased"] = split
         del w, res
     return out
 

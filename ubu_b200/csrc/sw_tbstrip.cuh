@@ -60,6 +60,7 @@ struct StripArgs {
   unsigned char* hstore;          // [warps of the grid] x tbs_hstore_bytes_per_warp
   uint2* boundary;                // [warps of the grid] x tbs_boundary_bytes_per_warp
   int rows_cap, bw_cap;
+  size_t h_stride, b_stride;      // bytes per warp of hstore / boundary (>= tbs_*_bytes_per_warp)
 };
 
 template <bool HAS_N, bool DEFAULT_SC, int BYTES>
@@ -77,8 +78,8 @@ tb_strip_kernel(TbArgs a, StripArgs sa) {
   const uint32_t MM4 = mmb * 0x01010101u, MX = mab ^ mmb, N4 = ((uint32_t)oe & 0xFFu) * 0x01010101u;
   const uint32_t NEG_OE = DEFAULT_SC ? 0xFFF9FFF9u : sc.neg_oe2, NEG_EXT = DEFAULT_SC ? 0xFFFEFFFEu : sc.neg_ext2,
                  POS_OE = DEFAULT_SC ? 0x00070007u : sc.pos_oe2;
-  unsigned char* hwarp = sa.hstore + (size_t)warp_global * tbs_hstore_bytes_per_warp(sa.rows_cap, sa.bw_cap, BYTES);
-  uint2* bnd = sa.boundary + (size_t)warp_global * (tbs_boundary_bytes_per_warp(sa.rows_cap, sa.bw_cap) / 8u) + lane;
+  unsigned char* hwarp = sa.hstore + (size_t)warp_global * sa.h_stride;
+  uint2* bnd = sa.boundary + (size_t)warp_global * (sa.b_stride / 8u) + lane;
   uint4* hlane = reinterpret_cast<uint4*>(hwarp) + lane;         // chunk (step, c) of this lane at hlane[(step * CHUNKS + c) * 32]
   uint32_t opbuf[TBS_BW_MAX + 16];                               // CIGAR runs of one walk (local memory; <= 2 * gaps + 3 <= bw + 2 runs)
   // boundary staging: per warp a double buffer of 16 steps x 32 lanes x 8 bytes

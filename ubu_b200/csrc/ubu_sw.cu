@@ -101,7 +101,7 @@ struct Slot {
   int tb_grid = 1;                       // CTAs of the register-band kernels (sized by the batch)
   StripCaps caps{0, 0};
   DevBuf<unsigned char> d_strip;         // H store + boundary arrays of the strip kernel's warps
-  struct StripLaunch { int grid = 0, bw_cap = 0, cls_lo = 0, cls_hi = 0; size_t h_off = 0, b_off = 0; } strip[2];   // common widths | very wide
+  struct StripLaunch { int grid = 0, bw_cap = 0, cls_lo = 0, cls_hi = 0; size_t h_off = 0, b_off = 0, h_stride = 0, b_stride = 0; } strip[2];   // common widths | very wide
   int strip_bytes = 1;
   int tbw_grid = 1;
   bool pre_queued = false; size_t pre_words = 0;   // early device->host copies queued by submit()
@@ -576,6 +576,7 @@ int do_stage(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw_s
         if (k == 1 && s.caps.bw_cap <= kStripBwCommon) continue;            // no band of this batch can be that wide
         const size_t per_warp_h = tbs_hstore_bytes_per_warp(s.caps.rows_cap, L.bw_cap, s.strip_bytes),
                      per_warp_b = tbs_boundary_bytes_per_warp(s.caps.rows_cap, L.bw_cap);
+        L.h_stride = per_warp_h; L.b_stride = per_warp_b;
         const size_t per_cta = (per_warp_h + per_warp_b) * (TBS_THREADS / 32);
         // the wide launch sees ~2 % of an indel-rich batch: a quarter of the SMs' worth of CTAs is plenty
         size_t grid = std::min<size_t>(k == 0 ? (size_t)h->sm_count * TBS_GRID_PER_SM : (size_t)(h->sm_count + 1) / 2, strip_ctas);
@@ -663,8 +664,9 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   // grid, underneath the forward launches of group g+1; only the last group's traceback stays exposed (cfg4, 1M reads: 25.6 - 28.9 ms
   // box to box -> 24.6 ms). Batches with one or a few forward launches run unphased: with 2 launches cfg3 gains 0.7 % and cfg2+N loses
   // 3 % (a reduced-grid phase outlives the short forward launch behind it), profiles/tb_phases_r02.txt.
-  static const int phases_env = [] { const char* v = getenv("UBU_TB_PHASES"); return v && *v ? std::max(1, std::min(kTbPhases, atoi(v))) : 0; }();
-  static const int gdiv_env = [] { const char* v = getenv("UBU_TB_PHASE_GRID_DIV"); return v && *v ? std::max(1, atoi(v)) : 3; }();
+  // (development switches, read per run so that a bench can time the phased and the unphased form of one staged batch)
+  const int phases_env = [] { const char* v = getenv("UBU_TB_PHASES"); return v && *v ? std::max(1, std::min(kTbPhases, atoi(v))) : 0; }();
+  const int gdiv_env = [] { const char* v = getenv("UBU_TB_PHASE_GRID_DIV"); return v && *v ? std::max(1, atoi(v)) : 3; }();
   int n_phases = 1;
   if (phases_env) { if (s.launches.size() > 1) n_phases = std::min<int>(phases_env, (int)s.launches.size()); }   // development switch
   else if (s.n_tasks >= (256u << 10) && s.launches.size() >= 8)
@@ -688,9 +690,26 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   static const bool tb_serial_env = env_off("UBU_TB_SERIAL");  // development switch: always one after the other
   const bool tb_serial = tb_serial_env || s.n_tasks >= (3u << 20);
   const bool phased = n_phases > 1;
-  cudaStream_t ax[kAux], dg;                                    // dg: the diagonal class
-  for (int k = 0; k < kAux; ++k) ax[k] = tb_serial ? (phased ? s.aux[0] : st) : s.aux[k];
-  dg = phased ? ax[0] : st;
+  // Which stream each traceback kernel goes to (issue order below = execution order within a stream: wide strips, common strips,
+  // band 32, 16, 8, diagonal, scalar). Uniform-length batches (few forward launches, narrow bands): the register-band kernels side by
+  // side, the strip launches on streams of their own (they see a handful of tasks and must not hold anything back). Mixed-length
+  // batches (>= 8 forward launches: cfg4), where the strip kernel is most of the traceback: the two store-heavy kernels one after
+  // the other on one stream (common strips, then band 32), everything light on a second one. With five streams per slot the first form
+  // also depends on which hardware queues the streams share (cfg4: 6.7 - 10.4 ms between handles of ONE process, a fixed sequence);
+  // the second gives 6.6 ms on every handle (profiles/tb_phases_r02.txt). Small mixed batches keep the first form: their tails matter
+  // more (cfg4 at 100k reads: 3.8 - 4.5 ms, mean 4.0, vs 4.1 - 4.2).
+  enum { K_DIAG, K_8, K_16, K_32, K_S0, K_S1, K_W, K_LONG, K_N };
+  const int sched_env = [&] { const char* v = getenv("UBU_TB_SCHED"); return v && *v ? atoi(v) : -1; }();     // development switch: 0 / 7
+  const int sched = sched_env >= 0 ? sched_env : (s.n_tasks >= (256u << 10) && s.launches.size() >= 8 ? 7 : 0);
+  cudaStream_t ks[K_N];
+  if (tb_serial) for (int k = 0; k < K_N; ++k) ks[k] = phased ? s.aux[0] : st;
+  else if (sched == 7) {
+    for (int k = 0; k < K_N; ++k) ks[k] = s.aux[1];
+    ks[K_S0] = s.aux[0]; ks[K_32] = s.aux[0]; ks[K_DIAG] = phased ? s.aux[2] : st;
+  } else {
+    ks[K_DIAG] = phased ? s.aux[0] : st; ks[K_8] = ks[K_16] = ks[K_LONG] = s.aux[0]; ks[K_32] = ks[K_W] = s.aux[1];
+    ks[K_S0] = s.aux[2]; ks[K_S1] = s.aux[3];
+  }
   const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
   const size_t selsz = s.any_n ? 4 : 2;
   const size_t sm8 = (size_t)(max_rows + 8) * TB_THREADS * selsz, sm16 = (size_t)(max_rows + 16) * TB_THREADS * selsz,
@@ -715,19 +734,28 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     if (last) CU(h, cudaEventRecord(s.ev[1], st));
     CU(h, cudaEventRecord(s.ev_fork, st));
     for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
-    if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, dg>>>(a, s.d_lists.p, first, count);
-    else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, dg>>>(a, s.d_lists.p, first, count);
-    CU(h, cudaGetLastError()); ++s.n_launches;
-    {
+    auto issue_strip = [&](int k) -> int {             // wide bands: the rare very wide ones (k = 1) are issued first
+      const Slot::StripLaunch& L = s.strip[k];
+      if (L.grid <= 0) return UBU_SW_OK;
+      StripArgs sa;
+      sa.lists = s.d_lists.p; sa.firsts = first; sa.counts = count; sa.work = s.d_ctr.p + CTR_STRIP_WORK + 2 * g + k; sa.n_slots = s.n_slots;
+      sa.cls_lo = L.cls_lo; sa.cls_hi = L.cls_hi;
+      sa.hstore = s.d_strip.p + L.h_off; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + L.b_off);
+      sa.rows_cap = s.caps.rows_cap; sa.bw_cap = L.bw_cap; sa.h_stride = L.h_stride; sa.b_stride = L.b_stride;
+      CU(h, launch_strip(s.any_n, def, s.strip_bytes, std::max(1, L.grid / gdiv), a, sa, k == 0 ? ks[K_S0] : ks[K_S1]));
+      ++s.n_launches;
+      return UBU_SW_OK;
+    };
+    auto issue_reg = [&]() -> int {
       auto launch3 = [&](auto k8, auto k16, auto k32) -> int {
         if (sm32 > 48 * 1024) {
           CU(h, cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
           CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
           CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         }
-        k8<<<grid, TB_THREADS, sm8, ax[0]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError());
-        k16<<<grid, TB_THREADS, sm16, ax[0]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError());
-        k32<<<grid, TB_THREADS, sm32, ax[1]>>>(a, s.d_lists.p + 3 * NS, first + 3, count + 3, h32, max_rows); CU(h, cudaGetLastError());
+        k32<<<grid, TB_THREADS, sm32, ks[K_32]>>>(a, s.d_lists.p + 3 * NS, first + 3, count + 3, h32, max_rows); CU(h, cudaGetLastError());
+        k16<<<grid, TB_THREADS, sm16, ks[K_16]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError());
+        k8<<<grid, TB_THREADS, sm8, ks[K_8]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError());
         return UBU_SW_OK;
       };
       int rc3;
@@ -737,19 +765,13 @@ int do_run(ubu_sw_handle* h, Slot& s) {
       else rc3 = launch3(tb_fill_reg_kernel<8, false, TB_THREADS, 2>, tb_fill_reg_kernel<16, false, TB_THREADS, 2>, tb_fill_reg_kernel<32, false, TB_THREADS, 2>);
       if (rc3) return rc3;
       s.n_launches += 3;
-    }
-    for (int k = 1; k >= 0; --k) {                       // wide bands: the rare very wide ones first, then the common widths
-      const Slot::StripLaunch& L = s.strip[k];
-      if (L.grid <= 0) continue;
-      StripArgs sa;
-      sa.lists = s.d_lists.p; sa.firsts = first; sa.counts = count; sa.work = s.d_ctr.p + CTR_STRIP_WORK + 2 * g + k; sa.n_slots = s.n_slots;
-      sa.cls_lo = L.cls_lo; sa.cls_hi = L.cls_hi;
-      sa.hstore = s.d_strip.p + L.h_off; sa.boundary = reinterpret_cast<uint2*>(s.d_strip.p + L.b_off);
-      sa.rows_cap = s.caps.rows_cap; sa.bw_cap = L.bw_cap;
-      CU(h, launch_strip(s.any_n, def, s.strip_bytes, std::max(1, L.grid / gdiv), a, sa, k == 0 ? ax[2] : ax[3]));
-      ++s.n_launches;
-    }
-    tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ax[1]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, first + TB_CLASS_SCALAR, count + TB_CLASS_SCALAR,
+      return UBU_SW_OK;
+    };
+    { int rc = issue_strip(1); if (!rc) rc = issue_strip(0); if (!rc) rc = issue_reg(); if (rc) return rc; }
+    if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
+    else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
+    CU(h, cudaGetLastError()); ++s.n_launches;
+    tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ks[K_W]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, first + TB_CLASS_SCALAR, count + TB_CLASS_SCALAR,
                                                             s.d_wide.p, max_rows, s.bw_cap);
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
@@ -757,8 +779,8 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     LongArgs la;
     la.list = s.d_order.p + s.n_slots; la.n = (uint32_t)s.long_tasks.size(); la.work = s.d_ctr.p + CTR_WORK + 2;
     la.scratch = s.d_long.p; la.per_warp = s.long_per_warp;
-    if (s.any_n) sw_long_kernel<true><<<s.long_grid, LONG_THREADS, 0, ax[0]>>>(a, la);
-    else sw_long_kernel<false><<<s.long_grid, LONG_THREADS, 0, ax[0]>>>(a, la);
+    if (s.any_n) sw_long_kernel<true><<<s.long_grid, LONG_THREADS, 0, ks[K_LONG]>>>(a, la);
+    else sw_long_kernel<false><<<s.long_grid, LONG_THREADS, 0, ks[K_LONG]>>>(a, la);
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
   for (int k = 0; k < kAux; ++k) {                    // join
