@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """EVERY record and CIGAR of a BASELINE config at its full size against the CPU oracle (all host cores), not a sample.
 
-    python tools/check_full.py cfg2 cfg4 cfg3 > profiles/full_check_rNN.jsonl
+    python tools/check_full.py [--resident] cfg2 cfg4 cfg3 > profiles/full_check_rNN.jsonl
+--resident: through ubu_sw_stage / run / fetch (one resident batch: the path that runs a large mixed-length batch's traceback in
+phases) instead of one ubu_sw_align_batch call (which streams the batch through the slots in chunks).
 cfg3 (5M reads, 1.5e12 cells) costs the oracle a few minutes on 16-32 cores; the others seconds."""
 import ctypes as C
 import json
@@ -42,10 +44,16 @@ def main():
               "cfg2+N": lambda: WL.with_n(WL.uniform("cfg2", 1_000_000, 76, 500, seed=5, paired=True, keep_codes=True), 0.005)}
     threads = os.cpu_count() or 1
     with U.SwAligner(device=0, slots=4) as al:
-        for name in sys.argv[1:]:
+        resident = "--resident" in sys.argv[1:]
+        for name in [a for a in sys.argv[1:] if not a.startswith("--")]:
             w = makers[name]()
             n = w.n_tasks
-            t0 = time.time(); got = al.align(w.reads, w.windows, w.pair_ref_idx); t_gpu = time.time() - t0
+            t0 = time.time()
+            if resident:
+                al.stage(0, w.reads, w.windows, w.pair_ref_idx); al.run(0); al.sync(0); got = al.fetch(0, n)
+            else:
+                got = al.align(w.reads, w.windows, w.pair_ref_idx)
+            t_gpu = time.time() - t0
             q, qoff = flat(w.reads); r, roff = flat(w.windows)
             rl, wl = w.reads.len.astype(np.uint32), w.windows.len.astype(np.uint32)
             idx = None if w.pair_ref_idx is None else np.ascontiguousarray(w.pair_ref_idx, dtype=np.uint32)
@@ -69,7 +77,7 @@ def main():
             k = np.arange(int(cn.sum())) - np.concatenate([[0], np.cumsum(cn)[:-1]])[task]
             diff = got.cigar_pool[g["cigar_off"].astype(np.int64)[task] + k] != cig[task * stride + k]
             bad[np.unique(task[diff])] = True
-            print(json.dumps({"config": name, "records": n, "cells": int(w.cells), "records_differing": int(bad.sum()),
+            print(json.dumps({"config": name, "path": "stage/run/fetch" if resident else "align_batch", "launches": al.last_run_launches(0) if resident else None, "records": n, "cells": int(w.cells), "records_differing": int(bad.sum()),
                               "cigar_ops_compared": int(cn.sum()), "gapped_records": int((res["cigar_n"] > 3).sum()),
                               "unaligned": int((res["flags"] & 1).sum()), "gpu_call_s": round(t_gpu, 3), "oracle_s": round(t_cpu, 1),
                               "oracle_threads": threads, "oracle_gcups": round(w.cells / t_cpu / 1e9, 2)}), flush=True)

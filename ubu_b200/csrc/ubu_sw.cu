@@ -662,7 +662,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   // forward launches) the launches are cut into groups of about equal cell count, and the traceback of group g (list entries [counts
   // after group g-1, counts after group g), from counter snapshots taken in stream order) runs on the side streams, at a third of its
   // grid, underneath the forward launches of group g+1; only the last group's traceback stays exposed (cfg4, 1M reads: 25.6 - 28.9 ms
-  // box to box -> 24.6 ms). Batches with one or a few forward launches run unphased: with 2 launches cfg3 gains 0.7 % and cfg2+N loses
+  // from handle to handle -> 23.6 ms with the stream schedule and the launch order below). Batches with one or a few forward launches run unphased: with 2 launches cfg3 gains 0.7 % and cfg2+N loses
   // 3 % (a reduced-grid phase outlives the short forward launch behind it), profiles/tb_phases_r02.txt.
   // (development switches, read per run so that a bench can time the phased and the unphased form of one staged batch)
   const int phases_env = [] { const char* v = getenv("UBU_TB_PHASES"); return v && *v ? std::max(1, std::min(kTbPhases, atoi(v))) : 0; }();
@@ -671,14 +671,20 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   if (phases_env) { if (s.launches.size() > 1) n_phases = std::min<int>(phases_env, (int)s.launches.size()); }   // development switch
   else if (s.n_tasks >= (256u << 10) && s.launches.size() >= 8)
     n_phases = (int)std::min<size_t>(std::min<size_t>(kTbPhases, s.launches.size() / 2), s.n_tasks >> 17);
-  std::vector<size_t> phase_end(n_phases, s.launches.size());         // phase g = launches [phase_end[g-1], phase_end[g])
+  // Phased batches run their forward launches longest reads first: the last group, whose traceback nothing hides, is then the one
+  // of the shortest reads (narrow bands, cheap traceback): cfg4 24.35 -> 23.6 ms. Groups of equal cell count (shrinking groups were tried:
+  // no gain, profiles/tb_phases_r02.txt).
+  std::vector<size_t> phase_end(n_phases, s.launches.size());         // phase g = launches fwd_order[phase_end[g-1] .. phase_end[g])
+  std::vector<size_t> fwd_order(s.launches.size());
+  for (size_t i = 0; i < fwd_order.size(); ++i) fwd_order[i] = i;
   if (n_phases > 1) {
+    if (!env_off("UBU_TB_PHASE_NOREV")) std::reverse(fwd_order.begin(), fwd_order.end());
     double total = 0, acc = 0;
     auto cost = [&](const FwdLaunch& L) { return (double)L.n_slots * kFwdCfgs[L.cfg].lmax * std::max(L.wmax, 1); };
     for (const FwdLaunch& L : s.launches) total += cost(L);
     int g = 0;
-    for (size_t i = 0; i < s.launches.size() && g + 1 < n_phases; ++i) {
-      acc += cost(s.launches[i]);
+    for (size_t i = 0; i < fwd_order.size() && g + 1 < n_phases; ++i) {
+      acc += cost(s.launches[fwd_order[i]]);
       if (acc >= total * (g + 1) / n_phases) phase_end[g++] = i + 1;
     }
     if (g > 0 && phase_end[g - 1] == s.launches.size()) --g;        // no forward launch left for a last group
@@ -721,7 +727,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   size_t li = 0;
   for (int g = 0; g < n_phases; ++g) {
     for (; li < phase_end[g]; ++li) {
-      CU(h, launch_fwd(s.launches[li], reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, plan, st));
+      CU(h, launch_fwd(s.launches[fwd_order[li]], reads, wins, idx, d_order, h->sc, s.d_fwd.p, s.d_gsel.p, plan, st));
       ++s.n_launches;
     }
     const bool last = g + 1 == n_phases;
