@@ -87,6 +87,7 @@ struct FwdLaunch { int cfg; bool has_n; uint32_t begin, n_slots; int wmax; uint3
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaStream_t hi[kAux] = {};                            // side streams above the main stream's priority, for traceback phases (made on first use)
   cudaStream_t aux[kAux] = {};                           // the traceback classes are independent: they run side by side
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
@@ -134,7 +135,7 @@ struct Slot {
 }  // namespace
 
 struct ubu_sw_handle {
-  int device = 0, n_slots = 2, sm_count = 148;
+  int device = 0, n_slots = 2, sm_count = 148, prio_hi = 0;
   Scoring sc = make_scoring(1, -3, 5, 2);
   Slot slots[kMaxSlots];
   std::string last_error;
@@ -707,14 +708,20 @@ int do_run(ubu_sw_handle* h, Slot& s) {
   enum { K_DIAG, K_8, K_16, K_32, K_S0, K_S1, K_W, K_LONG, K_N };
   const int sched_env = [&] { const char* v = getenv("UBU_TB_SCHED"); return v && *v ? atoi(v) : -1; }();     // development switch: 0 / 7
   const int sched = sched_env >= 0 ? sched_env : (s.n_tasks >= (256u << 10) && s.launches.size() >= 8 ? 7 : 0);
+  // A traceback phase underneath later forward launches must get its CTAs placed: phased batches use side streams above the main
+  // stream's priority (cfg4: 23.6 vs 24.4 ms). Everything else stays on streams of equal priority: the streamed chunks of the
+  // end-to-end path lose 1.3 % when each chunk's traceback pushes in front of the next chunk's forward pass.
+  if (phased)
+    for (int k = 0; k < kAux; ++k) if (!s.hi[k]) CU(h, cudaStreamCreateWithPriority(&s.hi[k], cudaStreamNonBlocking, h->prio_hi));
+  cudaStream_t* const sx = phased ? s.hi : s.aux;
   cudaStream_t ks[K_N];
-  if (tb_serial) for (int k = 0; k < K_N; ++k) ks[k] = phased ? s.aux[0] : st;
+  if (tb_serial && sched_env < 0) for (int k = 0; k < K_N; ++k) ks[k] = phased ? sx[0] : st;
   else if (sched == 7) {
-    for (int k = 0; k < K_N; ++k) ks[k] = s.aux[1];
-    ks[K_S0] = s.aux[0]; ks[K_32] = s.aux[0]; ks[K_DIAG] = phased ? s.aux[2] : st;
+    for (int k = 0; k < K_N; ++k) ks[k] = sx[1];
+    ks[K_S0] = sx[0]; ks[K_32] = sx[0]; ks[K_DIAG] = phased ? sx[2] : st;
   } else {
-    ks[K_DIAG] = phased ? s.aux[0] : st; ks[K_8] = ks[K_16] = ks[K_LONG] = s.aux[0]; ks[K_32] = ks[K_W] = s.aux[1];
-    ks[K_S0] = s.aux[2]; ks[K_S1] = s.aux[3];
+    ks[K_DIAG] = phased ? sx[0] : st; ks[K_8] = ks[K_16] = ks[K_LONG] = sx[0]; ks[K_32] = ks[K_W] = sx[1];
+    ks[K_S0] = sx[2]; ks[K_S1] = sx[3];
   }
   const bool def = h->sc.match == 1 && h->sc.mismatch == -3 && h->sc.gap_open == 5 && h->sc.gap_ext == 2;
   const size_t selsz = s.any_n ? 4 : 2;
@@ -739,7 +746,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     if (!last) CU(h, cudaMemcpyAsync(s.d_ctr.p + CTR_SNAP + 16 * g, s.d_ctr.p, TB_CLASSES * sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
     if (last) CU(h, cudaEventRecord(s.ev[1], st));
     CU(h, cudaEventRecord(s.ev_fork, st));
-    for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(s.aux[k], s.ev_fork, 0));
+    for (int k = 0; k < kAux; ++k) CU(h, cudaStreamWaitEvent(sx[k], s.ev_fork, 0));
     auto issue_strip = [&](int k) -> int {             // wide bands: the rare very wide ones (k = 1) are issued first
       const Slot::StripLaunch& L = s.strip[k];
       if (L.grid <= 0) return UBU_SW_OK;
@@ -759,9 +766,11 @@ int do_run(ubu_sw_handle* h, Slot& s) {
           CU(h, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
           CU(h, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         }
+        if (sched != 7) { k8<<<grid, TB_THREADS, sm8, ks[K_8]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError()); }
+        if (sched != 7) { k16<<<grid, TB_THREADS, sm16, ks[K_16]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError()); }
         k32<<<grid, TB_THREADS, sm32, ks[K_32]>>>(a, s.d_lists.p + 3 * NS, first + 3, count + 3, h32, max_rows); CU(h, cudaGetLastError());
-        k16<<<grid, TB_THREADS, sm16, ks[K_16]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError());
-        k8<<<grid, TB_THREADS, sm8, ks[K_8]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError());
+        if (sched == 7) { k16<<<grid, TB_THREADS, sm16, ks[K_16]>>>(a, s.d_lists.p + 2 * NS, first + 2, count + 2, h16, max_rows); CU(h, cudaGetLastError()); }
+        if (sched == 7) { k8<<<grid, TB_THREADS, sm8, ks[K_8]>>>(a, s.d_lists.p + 1 * NS, first + 1, count + 1, h8, max_rows); CU(h, cudaGetLastError()); }
         return UBU_SW_OK;
       };
       int rc3;
@@ -773,10 +782,21 @@ int do_run(ubu_sw_handle* h, Slot& s) {
       s.n_launches += 3;
       return UBU_SW_OK;
     };
-    { int rc = issue_strip(1); if (!rc) rc = issue_strip(0); if (!rc) rc = issue_reg(); if (rc) return rc; }
-    if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
-    else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
-    CU(h, cudaGetLastError()); ++s.n_launches;
+    auto issue_diag = [&]() -> int {
+      if (s.any_n) tb_diag_kernel<true><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
+      else tb_diag_kernel<false><<<h->sm_count * 8, 128, 0, ks[K_DIAG]>>>(a, s.d_lists.p, first, count);
+      CU(h, cudaGetLastError()); ++s.n_launches;
+      return UBU_SW_OK;
+    };
+    // issue order (it is the execution order within a stream, and earlier launches get their CTAs placed first). Side-by-side form:
+    // diagonal, band 8, 16, 32, strips -- the streamed chunks of the end-to-end path lose 2.6 % with the heavy kernels issued first.
+    // Two-stream form: wide strips, common strips, band 32, 16, 8, diagonal.
+    {
+      int rc = UBU_SW_OK;
+      if (sched == 7) { rc = issue_strip(1); if (!rc) rc = issue_strip(0); if (!rc) rc = issue_reg(); if (!rc) rc = issue_diag(); }
+      else { rc = issue_diag(); if (!rc) rc = issue_reg(); if (!rc) rc = issue_strip(1); if (!rc) rc = issue_strip(0); }
+      if (rc) return rc;
+    }
     tb_wide_kernel<<<s.tbw_grid, TBW_THREADS, 0, ks[K_W]>>>(a, s.d_lists.p + (size_t)TB_CLASS_SCALAR * NS, first + TB_CLASS_SCALAR, count + TB_CLASS_SCALAR,
                                                             s.d_wide.p, max_rows, s.bw_cap);
     CU(h, cudaGetLastError()); ++s.n_launches;
@@ -790,7 +810,7 @@ int do_run(ubu_sw_handle* h, Slot& s) {
     CU(h, cudaGetLastError()); ++s.n_launches;
   }
   for (int k = 0; k < kAux; ++k) {                    // join
-    CU(h, cudaEventRecord(s.ev_join[k], s.aux[k]));
+    CU(h, cudaEventRecord(s.ev_join[k], sx[k]));
     CU(h, cudaStreamWaitEvent(st, s.ev_join[k], 0));
   }
   CU(h, cudaEventRecord(s.ev[2], st));
@@ -899,17 +919,18 @@ int ubu_sw_create(const ubu_sw_params* params, int device, int slots, ubu_sw_han
   h->device = device; h->n_slots = slots; h->sm_count = prop.multiProcessorCount;
   h->sc = make_scoring(p.match, p.mismatch, p.gap_open, p.gap_ext);
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return UBU_SW_ERR_CUDA; }
-  int prio_lo = 0, prio_hi = 0;
-  if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_lo = prio_hi = 0; }
-  if (env_off("UBU_TB_NOPRIO")) prio_hi = prio_lo;              // development switch
+  {
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_lo = prio_hi = 0; }
+    h->prio_hi = env_off("UBU_TB_NOPRIO") ? prio_lo : prio_hi;  // development switch
+  }
   for (int i = 0; i < slots; ++i) {
-    if (cudaStreamCreateWithPriority(&h->slots[i].stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     for (int e = 0; e < 3; ++e)
       if (cudaEventCreate(&h->slots[i].ev[e]) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&h->slots[i].ev_fork, cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     for (int e = 0; e < kAux; ++e) {
-      // side streams above the main stream's priority: a traceback phase running underneath later forward launches gets its CTAs placed
-      if (cudaStreamCreateWithPriority(&h->slots[i].aux[e], cudaStreamNonBlocking, prio_hi) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
+      if (cudaStreamCreateWithFlags(&h->slots[i].aux[e], cudaStreamNonBlocking) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
       if (cudaEventCreateWithFlags(&h->slots[i].ev_join[e], cudaEventDisableTiming) != cudaSuccess) { ubu_sw_destroy(h); return UBU_SW_ERR_CUDA; }
     }
   }
@@ -932,7 +953,7 @@ void ubu_sw_destroy(ubu_sw_handle* h) {
     if (i == 0) { h->g_packed.release(); h->g_nmask.release(); h->p_bytes.release(); h->g_off.release(); h->g_noff.release(); h->g_len.release(); h->p_words.release(); }
     for (int e = 0; e < 3; ++e) if (s.ev[e]) cudaEventDestroy(s.ev[e]);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-    for (int e = 0; e < kAux; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); }
+    for (int e = 0; e < kAux; ++e) { if (s.ev_join[e]) cudaEventDestroy(s.ev_join[e]); if (s.aux[e]) cudaStreamDestroy(s.aux[e]); if (s.hi[e]) cudaStreamDestroy(s.hi[e]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   delete h;
@@ -1247,7 +1268,7 @@ void multi_worker(MultiRun* R, int d) {
   const int nd = (int)R->m->hs.size();
   if (cudaSetDevice(h->device) != cudaSuccess) { R->fail(UBU_SW_ERR_CUDA); return; }
   int head = 0, inflight = 0;
-  uint32_t chunk_of_slot[kMaxSlots];
+  uint32_t chunk_of_slot[kMaxSlots] = {};
   auto finish = [&](int slot) -> int {
     Slot& s = h->slots[slot];
     const uint32_t c = chunk_of_slot[slot];
