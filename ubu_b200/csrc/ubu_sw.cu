@@ -118,7 +118,7 @@ struct Slot {
   std::vector<FwdLaunch> launches;
   std::vector<uint32_t> long_tasks;      // reads beyond the packed classes (L > 256): sw_long_kernel, one warp per task
   DevBuf<unsigned char> d_long; size_t long_per_warp = 0; int long_grid = 0;
-  std::vector<uint32_t> tmp_keys, tmp_end, plain_order;     // plain_order: the order array when planning without a device
+  std::vector<uint32_t> tmp_keys, tmp_end, tmp_sort, tmp_hist, plain_order;     // plain_order: the order array when planning without a device
   // staged batch
   bool staged = false, ran = false, pending = false;
   uint32_t n_tasks = 0, n_slots = 0;
@@ -191,9 +191,14 @@ inline bool ascending(const uint32_t* off, const uint16_t* len, uint32_t m, uint
   return (cpu_has_avx2() ? ascending_avx2(off, len, m, per) : ascending_body(off, len, m, per)) == 0u;
 }
 
-int cfg_of_len(int L) {
-  for (int c = 0; c < kNumCfgs; ++c) if (L <= kFwdCfgs[c].lmax) return c;
-  return -1;
+int cfg_of_len(int L) {                 // read-length class of a read of L bases (-1: longer than the packed kernels take)
+  static const std::vector<int8_t> lut = [] {
+    std::vector<int8_t> t((size_t)kFwdCfgs[kNumCfgs - 1].lmax + 1, (int8_t)-1);
+    for (int len = 0; len < (int)t.size(); ++len)
+      for (int c = 0; c < kNumCfgs; ++c) if (len <= kFwdCfgs[c].lmax) { t[len] = (int8_t)c; break; }
+    return t;
+  }();
+  return L >= 0 && L < (int)lut.size() ? lut[L] : -1;
 }
 
 int sel_stride_for(int wmax, int G) { return ((wmax + 2 * G + 63) / 64) * 64 + G; }
@@ -462,7 +467,16 @@ int plan_batch(ubu_sw_handle* h, Slot& s, const ubu_sw_seqs* reads, const ubu_sw
     if (!cnt[b]) continue;
     uint32_t* lo = order + start[b];
     if (wmin[b] != wmaxv[b]) {
-      std::stable_sort(lo, lo + cnt[b], [&](uint32_t x, uint32_t y) { return (s.tmp_keys[x] & 0xFFFFu) < (s.tmp_keys[y] & 0xFFFFu); });
+      // stable counting sort by window length (this runs per streamed chunk, in front of its upload: a comparison sort through the
+      // key array cost more host time than the chunk takes on the GPU)
+      const uint32_t range = (uint32_t)(wmaxv[b] - wmin[b]) + 1u;
+      s.tmp_hist.assign((size_t)range + 1, 0u);
+      s.tmp_sort.resize(cnt[b]);
+      uint32_t* hist = s.tmp_hist.data();
+      for (uint32_t k = 0; k < cnt[b]; ++k) ++hist[(s.tmp_keys[lo[k]] & 0xFFFFu) - (uint32_t)wmin[b] + 1u];
+      for (uint32_t r = 0; r < range; ++r) hist[r + 1] += hist[r];
+      for (uint32_t k = 0; k < cnt[b]; ++k) s.tmp_sort[hist[(s.tmp_keys[lo[k]] & 0xFFFFu) - (uint32_t)wmin[b]]++] = lo[k];
+      std::copy(s.tmp_sort.begin(), s.tmp_sort.end(), lo);
     }
     const int cfg = b / 2; const bool has_n = b & 1;
     const uint32_t total = (cnt[b] + 1u) & ~1u;
@@ -1058,7 +1072,15 @@ int align_stream(ubu_sw_handle* h, const ubu_sw_seqs* reads, const ubu_sw_seqs* 
   if (h->n_slots < 2 || n < kStreamMinReads || !out) return kNoStream;
   for (int k = 0; k < h->n_slots; ++k) if (h->slots[k].pending) return kNoStream;
   if (validate_seqs(reads) || validate_seqs(wins) || (!idx && reads->count != wins->count)) return kNoStream;   // the one-shot path reports it
-  const uint32_t chunk = std::min(kStreamChunkMax, std::max(kStreamChunkMin, n / (uint32_t)(2 * h->n_slots)));
+  uint32_t chunk = std::min(kStreamChunkMax, std::max(kStreamChunkMin, n / (uint32_t)(2 * h->n_slots)));
+  {
+    // Mixed read lengths (judged on the first reads): a chunk is a dozen or more forward launches, and from 256k reads on its traceback
+    // runs in phases underneath them (do_run): larger chunks (cfg4, 4M reads from pinned host buffers: 110 -> 102 ms).
+    uint16_t lmin = 0xFFFF, lmax = 0;
+    minmax_u16(reads->len, std::min<uint32_t>(n, 1u << 16), lmin, lmax);
+    if (cfg_of_len(lmin) != cfg_of_len(lmax)) chunk = std::min(1u << 18, std::max(1u << 16, n / (uint32_t)h->n_slots));
+  }
+  if (const char* v = getenv("UBU_STREAM_CHUNK")) if (*v) chunk = std::max<uint32_t>(1024u, (uint32_t)atol(v));   // development switch
   // What streaming needs is checked chunk by chunk, right before a chunk is staged (a pass over the whole batch up front
   // would sit in front of the first upload): its reads and the windows they use are laid out in ascending order, so that
   // one stretch of bytes holds them all, and the windows form a compact stretch (reads grouped by window, as
