@@ -247,6 +247,31 @@ def test_cfg4_300k_resident_batch_runs_its_traceback_in_phases(aligner):
         check_every_record_fast(al, w)
 
 
+def test_phased_batch_with_contig_sized_reads(aligner):
+    """A phased batch (280k mixed-length reads) that also holds contig-sized reads: sw_long_kernel runs on the phases' side streams
+    behind the last group. The short records must equal those of the batch without the long reads, the long ones the oracle's."""
+    rng = np.random.default_rng(5)
+    w = WL.cfg4(280_000, tie_stress=2_000, seed=78)
+    big = "".join(rng.choice(list("ACGT"), size=3000))
+    long_reads = [_mutated(rng, big, L) for L in (300, 777, 1500, 2500, 257, 1024)]
+    lw = WL.Workload("long", U.pack_texts(long_reads), U.pack_texts([big]), np.zeros(len(long_reads), dtype=np.uint32), 0)
+    both = WL.concat("cfg4+long", [w, lw])
+    aligner.stage(0, w.reads, w.windows, w.pair_ref_idx); aligner.run(0); aligner.sync(0)
+    alone = aligner.fetch(0, w.n_tasks)
+    aligner.stage(0, both.reads, both.windows, both.pair_ref_idx); aligner.run(0); aligner.sync(0)
+    assert aligner.last_run_launches(0) >= 16 + 2 * 7 + 1
+    got = aligner.fetch(0, both.n_tasks)
+    n = w.n_tasks
+    for f in FIELDS + ("cigar_n", "flags"):
+        assert np.array_equal(got.results[f][:n], alone.results[f]), f
+    pick = rng.choice(n, size=2000, replace=False)
+    assert all(got.cigar(int(k)) == alone.cigar(int(k)) for k in pick)
+    from ubu_b200.seqs import codes_from_text
+    ores, ocig = O.align_batch([codes_from_text(r) for r in long_reads], [codes_from_text(big)] * len(long_reads), None, nthreads=8)
+    for j in range(len(long_reads)):
+        assert all(int(got.results[n + j][f]) == int(ores[j][f]) for f in FIELDS) and got.cigar(n + j) == ocig[j]
+
+
 def test_extreme_scoring_reaches_the_scalar_last_resort():
     """match 31 / ext 1 lets a low score afford thousands of gap bases: the band outgrows every packed class."""
     rng = np.random.default_rng(2)
