@@ -120,7 +120,9 @@ int ubu_sw_sync(ubu_sw_handle* h, int slot);
 int ubu_sw_fetch(ubu_sw_handle* h, int slot, ubu_sw_result* out,
                  uint32_t* cigar_pool, size_t cigar_pool_cap, size_t* cigar_pool_used);
 /* Device time in ms of the last run() on the slot (CUDA events on the slot's stream): [0] whole run,
- * [1] forward (score) kernels, [2] traceback + CIGAR kernels. Valid after sync(). */
+ * [1] forward (score) kernels, [2] traceback + CIGAR kernels. Valid after sync(). A large mixed-length batch
+ * runs the traceback of its earlier forward launches underneath the later ones: [1] is then
+ * the span of the forward launches with that traceback underneath, [2] the traceback left after them. */
 int ubu_sw_last_run_ms(ubu_sw_handle* h, int slot, float ms[3]);
 /* Number of kernel launches issued by the last run() on the slot. */
 int ubu_sw_last_run_launches(ubu_sw_handle* h, int slot);
