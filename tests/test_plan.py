@@ -145,3 +145,26 @@ def test_mixed_read_lengths_in_one_class_with_exactly_sized_buffers():
     rs.packed_bytes -= 1
     n_slots, nl = C.c_uint32(0), C.c_int(0)
     assert N.lib().ubu_sw_debug_plan(C.byref(rs), C.byref(ws), None, None, 0, C.byref(n_slots), None, None, 0, C.byref(nl)) == N.ERR_ARG
+
+
+def test_buckets_are_ordered_by_window_length_stably():
+    """Inside a read-length class the tasks are ordered by ascending window length (a pair, a CTA sweep similar widths), ties in input
+    order: the plan sorts with a counting sort over the bucket's window-length range, narrow or as wide as 16-bit lengths allow."""
+    rng = np.random.default_rng(12)
+    for wlo, whi in ((200, 1000), (1, 65535)):
+        n = 3000
+        rl = rng.integers(20, 257, size=n)
+        wl = rng.integers(wlo, whi + 1, size=n)
+        wl[rng.integers(0, n, size=n // 3)] = wlo + 7                              # many ties
+        reads = U.pack_codes([rng.integers(0, 4, size=int(l), dtype=np.uint8) for l in rl])
+        wins = U.pack_codes([rng.integers(0, 4, size=int(l), dtype=np.uint8) for l in wl])
+        order, ident, launches = plan(reads, wins, None)
+        assert not ident
+        check_invariants(reads, wins, None, order, launches)
+        by_rows = {}
+        for rows, has_n, first, slots, wmax, shared in launches:                   # a class may be split into several launches: join them
+            by_rows.setdefault(int(rows), []).extend(int(t) for t in order[first:first + slots] if t != PAD)
+        assert len(by_rows) > 10
+        for rows, tasks in by_rows.items():
+            keys = [(int(wl[t]), t) for t in tasks]
+            assert keys == sorted(keys), rows                                      # ascending window length, input order among equals
